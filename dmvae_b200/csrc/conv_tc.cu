@@ -1,0 +1,632 @@
+// tcgen05 implicit-GEMM convolution for sm_100a: the conv tiles of flux_ae's ResnetBlock / Upsample / AttnBlock
+// (models/flux_ae.py:32-35,63-67,101,210) in forward and data-gradient form.
+//
+//   D[pixel, co] = sum_{tap, ci} X[pixel (+) tap, ci] * Wp[tap][co][ci]          M = B*H*W, N = Cout, K = taps*Cin
+//
+// * A operand (activations, channels-last bf16 [B][H][W][C]) is fetched by a 4-D tiled TMA box
+//   {64 ch, BW, BH, 1} shifted by the filter tap; out-of-image coordinates are zero-filled by the TMA unit, which
+//   is exactly the conv's zero padding.  No im2col buffer exists anywhere.
+// * B operand (tap-major packed weights [tap][Cout][Cin]) is a 3-D TMA box {64, BN, 1}.
+// * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
+// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32) into a TMEM accumulator;
+//   two accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+// * Persistent: one CTA per SM walks tiles round-robin.  Warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+//   alloc), warps 2..5 = epilogue (tcgen05.ld -> +bias -> bf16 [-> +residual] -> 64-byte global stores).
+//
+// dgrad of a stride-1 "same" conv is the same kernel fed dY and the flipped/transposed weight pack.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <string.h>
+
+namespace {
+
+constexpr int BM = 128;        // pixels per tile (UMMA M)
+constexpr int BK = 64;         // channels per pipeline stage (one 128-byte swizzle row)
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcGeom {
+    int B, H, W, Cin, Cout, KH, KW, pt, pl;
+    int BW, BH;            // pixel tile = BH rows x BW cols of one image (BH*BW = 128)
+    int tiles_w, tiles_h;  // W/BW, H/BH
+    int m_tiles, n_tiles, k_chunks;
+};
+
+template <int BN> struct Cfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers (256 or 512 columns)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out, TcGeom g) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                       // [STAGES]
+    uint64_t* empty = bars + C::STAGES;          // [STAGES]
+    uint64_t* tfull = bars + 2 * C::STAGES;      // [2]
+    uint64_t* tempty = bars + 2 * C::STAGES + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = g.m_tiles * g.n_tiles;
+    const int k_iters = g.KH * g.KW * g.k_chunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
+                const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
+                const int w0 = tw * g.BW - g.pl, h0 = th * g.BH - g.pt, n0 = nt * BN;
+                for (int tap = 0; tap < g.KH * g.KW; ++tap) {
+                    const int kh = tap / g.KW, kw = tap % g.KW;
+                    for (int kc = 0; kc < g.k_chunks; ++kc) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                        uint8_t* sb = sa + C::A_BYTES;
+                        mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                        tma_load_4d(sa, &map_a, &full[stage], kc * BK, w0 + kw, h0 + kh, b);
+                        tma_load_3d(sb, &map_b, &full[stage], kc * BK, n0, tap);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int k = 0; k < k_iters; ++k) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + C::A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        // advance 16 elements (32 B) along K inside the swizzled row: +2 in 16-byte units
+                        umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+                    }
+                    umma_commit(&empty[stage]);                     // frees the smem slot when these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[buf]);                           // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5) ==============================
+        const int lg = warp & 3;                 // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
+        const int r = lg * 32 + lane;            // row of the tile = pixel index inside the tile
+        const int dh = r / g.BW, dw = r % g.BW;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
+            const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
+            const int64_t pix = ((int64_t)b * g.H + th * g.BH + dh) * g.W + tw * g.BW + dw;
+            const int n0 = nt * BN;
+            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                const int n = n0 + c0;
+                if (n >= g.Cout) continue;                            // warp-uniform
+                bf16* op = out + pix * g.Cout + n;
+                const bf16* rp = res ? res + pix * g.Cout + n : nullptr;
+                if (n + 32 <= g.Cout) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
+                        if (rp) {
+                            float fr[8];
+                            unpack_bf16x8(*reinterpret_cast<const uint4*>(rp + q * 8), fr);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];   // bf16 conv output, then bf16 add
+                        }
+                        *reinterpret_cast<uint4*>(op + q * 8) = pack_bf16x8(f);
+                    }
+                } else {
+                    for (int e = 0; e < 32 && n + e < g.Cout; ++e) {
+                        float f = __uint_as_float(v[e]) + (bias ? __ldg(bias + n + e) : 0.f);
+                        if (rp) f = bf16_round(f) + __bfloat162float(rp[e]);
+                        op[e] = __float2bfloat16_rn(f);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------- weight gradient
+// dWp[tap][co][ci] += sum_pixels dY[p][co] * X[p (+) tap][ci]          M = Cout, N = Cin, K = pixels (split)
+//
+// Both operands are "MN-major" for this GEMM (the contraction index -- pixels -- is the slow index of a
+// channels-last tensor), which tcgen05 consumes natively: the same {64 ch, BW, BH, 1} TMA boxes as the forward
+// pass land as [pixel][64 ch] 128-byte-swizzled rows, described to the MMA as MN-major atoms (8 x 128 B) with
+// LBO = distance between 64-channel boxes and SBO = 1024 B between 8-pixel groups.
+constexpr int WG_PIX = 64;                 // pixels (K) per pipeline stage
+constexpr int WG_BOX_BYTES = WG_PIX * 128; // one {64 ch x 64 px} box
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;       // LBO: next 64-channel atom along M/N
+    d |= (uint64_t)(1024 >> 4) << 32;               // SBO: next 8-pixel group along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int n) {
+    return make_idesc(n) | (1u << 15) | (1u << 16);   // A and B both MN-major
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct WgGeom {
+    int B, H, W, Cin, Cout, KH, KW, pt, pl;
+    int BW, BH, tiles_w, tiles_h;
+    int pix_tiles;          // B * tiles_h * tiles_w
+    int co_tiles, ci_tiles, splits, tiles_per_split;
+};
+
+template <int BN> struct WgCfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int A_BYTES = 2 * WG_BOX_BYTES;
+    static constexpr int B_BYTES = (BN / 64) * WG_BOX_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr uint32_t TMEM_COLS = BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                     float* __restrict__ dwp, WgGeom g) {
+    using C = WgCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::STAGES;
+    uint64_t* tfull = bars + 2 * C::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // blockIdx.x -> (co tile, ci tile, tap) ; blockIdx.y -> pixel split
+    int id = blockIdx.x;
+    const int co_t = id % g.co_tiles; id /= g.co_tiles;
+    const int ci_t = id % g.ci_tiles; id /= g.ci_tiles;
+    const int tap = id;
+    const int kh = tap / g.KW, kw = tap % g.KW;
+    const int co0 = co_t * BM, ci0 = ci_t * BN;
+    const int t_begin = blockIdx.y * g.tiles_per_split;
+    const int t_end = (t_begin + g.tiles_per_split < g.pix_tiles) ? t_begin + g.tiles_per_split : g.pix_tiles;
+    const int k_iters = t_end - t_begin;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_dy);
+        prefetch_tmap(&map_x);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, b = t / (g.tiles_w * g.tiles_h);
+                const int w0 = tw * g.BW, h0 = th * g.BH;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                uint8_t* sb = sa + C::A_BYTES;
+                mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) tma_load_4d(sa + j * WG_BOX_BYTES, &map_dy, &full[stage], co0 + j * 64, w0, h0, b);
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                    tma_load_4d(sb + j * WG_BOX_BYTES, &map_x, &full[stage], ci0 + j * 64, w0 + kw - g.pl, h0 + kh - g.pt, b);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_mn(BN);
+            int stage = 0; uint32_t phase = 0;
+            for (int k = 0; k < k_iters; ++k) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                const uint64_t adesc = make_mnmajor_sw128_desc(sa);
+                const uint64_t bdesc = make_mnmajor_sw128_desc(sa + C::A_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < WG_PIX / UMMA_K; ++kk) {
+                    // 16 pixels = 16 rows of 128 B = 2048 B along K: +128 in 16-byte units
+                    umma_bf16(tmem_base, adesc + 128 * kk, bdesc + 128 * kk, idesc, (k | kk) != 0);
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int lg = warp & 3;
+        const int co = co0 + lg * 32 + lane;
+        if (k_iters > 0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                const int ci = ci0 + c0;
+                if (co < g.Cout && ci < g.Cin) {
+                    float* dst = dwp + ((int64_t)tap * g.Cout + co) * g.Cin + ci;
+                    if (ci + 32 <= g.Cin) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    } else {
+                        for (int e = 0; e < 32 && ci + e < g.Cin; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------- host side: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+struct MapKey {
+    uint64_t v[8];
+    bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = 1469598103934665603ull;
+        for (int i = 0; i < 8; ++i) { h ^= k.v[i]; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+// bf16 tensor, rank 3 or 4, innermost dim contiguous, 128B swizzle, zero OOB fill
+int get_tensor_map(const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, CUtensorMap* out) {
+    MapKey key;
+    memset(&key, 0, sizeof(key));
+    key.v[0] = (uint64_t)(uintptr_t)ptr;
+    key.v[1] = (uint64_t)rank;
+    for (int i = 0; i < rank; ++i) key.v[2 + i] = dims[i] | ((uint64_t)box[i] << 40);
+    {
+        std::lock_guard<std::mutex> lk(g_map_mu);
+        auto itc = g_map_cache.find(key);
+        if (itc != g_map_cache.end()) { *out = itc->second; return DMVAE_OK; }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return dmvae_set_error(DMVAE_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[4]; cuuint64_t gstride[3]; cuuint32_t bdim[4]; cuuint32_t estride[4];
+    uint64_t stride = 2;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i]; bdim[i] = box[i]; estride[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstride[i] = stride;
+    }
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bdim, estride,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return dmvae_set_error(DMVAE_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (g_map_cache.size() > 4096) g_map_cache.clear();
+    g_map_cache.emplace(key, *out);
+    return DMVAE_OK;
+}
+
+int pick_pixel_tile(int H, int W, int* BW, int* BH) {
+    int bw = 1;
+    while (bw * 2 <= 128 && W % (bw * 2) == 0) bw *= 2;
+    const int bh = BM / bw;
+    if (bw < 8 || H % bh != 0 || bh > 256) return 0;
+    *BW = bw; *BH = bh;
+    return 1;
+}
+
+int g_num_sms = 0;
+
+template <int BN>
+int launch_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, TcGeom g, cudaStream_t st) {
+    using C = Cfg<BN>;
+    CUtensorMap ma, mb;
+    const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint32_t abox[4] = {BK, (uint32_t)g.BW, (uint32_t)g.BH, 1};
+    int rc = get_tensor_map(x, 4, adims, abox, &ma);
+    if (rc) return rc;
+    const uint64_t bdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, (uint64_t)(g.KH * g.KW)};
+    const uint32_t bbox[3] = {BK, BN, 1};
+    rc = get_tensor_map(w, 3, bdims, bbox, &mb);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return dmvae_set_error(DMVAE_ECUDA, "conv_tc: smem attribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    const int tiles = g.m_tiles * g.n_tiles;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, g);
+    DMVAE_CHECK_LAUNCH("conv_tc_kernel");
+    return DMVAE_OK;
+}
+
+}  // namespace
+
+// 1 if (shape) can run on the tcgen05 tile, else 0 (caller uses conv_direct)
+DMVAE_API int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW) {
+    int bw, bh;
+    if (B <= 0 || Cin % 8 != 0 || Cout % 8 != 0 || Cin < 32 || Cout < 32) return 0;
+    if (!((KH == 3 && KW == 3) || (KH == 1 && KW == 1))) return 0;
+    return pick_pixel_tile(H, W, &bw, &bh);
+}
+
+// stride-1 "same" convolution (3x3 pad 1 or 1x1 pad 0) on the tensor cores.
+//   y = conv(x, w_packed) + bias [; y = bf16(y) + residual]
+DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
+                                int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream) {
+    DMVAE_CHECK_ARG(x && w_packed && y, "conv_tc_fwd: null pointer");
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
+                    ((uintptr_t)residual & 15) == 0, "conv_tc_fwd: buffers must be 16-byte aligned");
+    if (!dmvae_conv_tc_supported(B, H, W, Cin, Cout, KH, KW))
+        return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_tc_fwd: shape B=%d H=%d W=%d Cin=%d Cout=%d k=%dx%d not supported", B, H, W, Cin, Cout, KH, KW);
+    TcGeom g;
+    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
+    g.pt = (KH - 1) / 2; g.pl = (KW - 1) / 2;
+    pick_pixel_tile(H, W, &g.BW, &g.BH);
+    g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
+    g.m_tiles = B * g.tiles_w * g.tiles_h;
+    g.k_chunks = (Cin + BK - 1) / BK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cout % 256 == 0 || Cout > 256) {
+        g.n_tiles = (Cout + 255) / 256;
+        return launch_conv_tc<256>(x, w_packed, bias, residual, y, g, st);
+    }
+    g.n_tiles = (Cout + 127) / 128;
+    return launch_conv_tc<128>(x, w_packed, bias, residual, y, g, st);
+}
+
+namespace {
+int pick_pixel_tile64(int H, int W, int* BW, int* BH) {
+    int bw = 1;
+    while (bw * 2 <= WG_PIX && W % (bw * 2) == 0) bw *= 2;
+    const int bh = WG_PIX / bw;
+    if (bw < 8 || H % bh != 0) return 0;
+    *BW = bw; *BH = bh;
+    return 1;
+}
+
+template <int BN>
+int launch_wgrad_tc(const void* x, const void* dy, float* dwp, WgGeom g, cudaStream_t st) {
+    using C = WgCfg<BN>;
+    CUtensorMap mdy, mx;
+    const uint32_t box[4] = {64, (uint32_t)g.BW, (uint32_t)g.BH, 1};
+    const uint64_t ddims[4] = {(uint64_t)g.Cout, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    int rc = get_tensor_map(dy, 4, ddims, box, &mdy);
+    if (rc) return rc;
+    const uint64_t xdims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    rc = get_tensor_map(x, 4, xdims, box, &mx);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return dmvae_set_error(DMVAE_ECUDA, "conv_tc_wgrad: smem attribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    g.ci_tiles = (g.Cin + BN - 1) / BN;
+    const int base = g.co_tiles * g.ci_tiles * g.KH * g.KW;
+    int splits = (148 + base - 1) / base;
+    if (splits > g.pix_tiles) splits = g.pix_tiles;
+    if (splits < 1) splits = 1;
+    g.tiles_per_split = (g.pix_tiles + splits - 1) / splits;
+    g.splits = (g.pix_tiles + g.tiles_per_split - 1) / g.tiles_per_split;
+    dim3 grid((unsigned)base, (unsigned)g.splits);
+    conv_tc_wgrad_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(mdy, mx, dwp, g);
+    DMVAE_CHECK_LAUNCH("conv_tc_wgrad_kernel");
+    return DMVAE_OK;
+}
+}  // namespace
+
+DMVAE_API int dmvae_conv_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW) {
+    int bw, bh;
+    if (B <= 0 || Cin % 8 != 0 || Cout % 8 != 0 || Cin < 32 || Cout < 32) return 0;
+    if (!((KH == 3 && KW == 3) || (KH == 1 && KW == 1))) return 0;
+    return pick_pixel_tile64(H, W, &bw, &bh);
+}
+
+// dw_tap_major[tap][Cout][Cin] (fp32) += sum_pixels dy[p][co] * x[p (+) tap][ci]
+DMVAE_API int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_major, int B, int H, int W, int Cin,
+                                  int Cout, int KH, int KW, void* stream) {
+    DMVAE_CHECK_ARG(x && dy && dw_tap_major, "conv_tc_wgrad: null pointer");
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dw_tap_major & 15) == 0,
+                    "conv_tc_wgrad: buffers must be 16-byte aligned");
+    if (!dmvae_conv_tc_wgrad_supported(B, H, W, Cin, Cout, KH, KW) || Cin % 4 != 0)
+        return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_tc_wgrad: shape B=%d H=%d W=%d Cin=%d Cout=%d k=%dx%d not supported", B, H, W, Cin, Cout, KH, KW);
+    WgGeom g;
+    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
+    g.pt = (KH - 1) / 2; g.pl = (KW - 1) / 2;
+    pick_pixel_tile64(H, W, &g.BW, &g.BH);
+    g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
+    g.pix_tiles = B * g.tiles_w * g.tiles_h;
+    g.co_tiles = (Cout + BM - 1) / BM;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin >= 256) return launch_wgrad_tc<256>(x, dy, dw_tap_major, g, st);
+    return launch_wgrad_tc<128>(x, dy, dw_tap_major, g, st);
+}

@@ -1,0 +1,296 @@
+// GroupNorm(32 groups, eps) + swish on channels-last bf16 activations, forward and backward.
+// Reference: models/flux_ae.py:21-22 (swish), :30,62,64,157,236 (GroupNorm(32, C, eps=1e-6)),
+// used as swish(norm(x)) in ResnetBlock.forward :69-77 and Decoder/Encoder tails :177-179,266-268;
+// AttnBlock uses the norm without swish (:38).  Under autocast the reference runs GroupNorm and swish
+// in fp32 and the following conv rounds its input to bf16: these kernels do the same (fp32 math,
+// fp64 statistics, one bf16 rounding at the store).
+//
+// Layout: x[b][pixel][c], c fastest.  HBM-bound: stats = 2 B/elem read; apply = 2 B read + 2 B write.
+#include "common.cuh"
+
+#define GN_GROUPS 32
+#define GN_THREADS 256
+
+struct GnGeom {
+    int vc;        // 16-byte vectors per pixel  (C / 8)
+    int rows;      // pixels handled per block pass (GN_THREADS / vc)
+};
+
+static int gn_geom(int C, GnGeom* g, const char* who) {
+    if (C % GN_GROUPS != 0 || C % 8 != 0 || C > 2048 || (GN_THREADS % (C / 8)) != 0)
+        return dmvae_set_error(DMVAE_EUNSUPPORTED, "%s: unsupported channel count %d (need C%%32==0, C/8 | 256)", who, C);
+    g->vc = C / 8;
+    g->rows = GN_THREADS / g->vc;
+    return DMVAE_OK;
+}
+
+static void gn_grid(int64_t B, int64_t HW, int rows, dim3* grid, int64_t* ppb) {
+    // aim for >= 4 waves of 148 SMs x 2 CTAs, but at least 4 passes of work per CTA
+    int64_t chunks = (148 * 8 + B - 1) / B;
+    int64_t max_chunks = ceil_div64(HW, (int64_t)rows * 4);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    *ppb = ceil_div64(HW, chunks);
+    chunks = ceil_div64(HW, *ppb);
+    *grid = dim3((unsigned)chunks, (unsigned)B);
+}
+
+// stats[b][g] = {sum, sumsq} (fp64, caller zero-initialised)
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats,
+                                                              int64_t HW, int C, int vc, int rows, int64_t ppb) {
+    __shared__ float s_acc[GN_GROUPS * 2];
+    const int b = blockIdx.y;
+    const int col = threadIdx.x % vc, row = threadIdx.x / vc;
+    const int cpg = C / GN_GROUPS;
+    if (threadIdx.x < GN_GROUPS * 2) s_acc[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int64_t p0 = (int64_t)blockIdx.x * ppb;
+    const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
+    float s[8], ss[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
+    const bf16* base = x + (int64_t)b * HW * C + col * 8;
+    for (int64_t p = p0 + row; p < p1; p += rows) {
+        float f[8];
+        unpack_bf16x8(ld_stream16(base + p * C), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] += f[k] * f[k]; }
+    }
+    if (cpg >= 8) {
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a += s[k]; q += ss[k]; }
+        const int g = (col * 8) / cpg;
+        atomicAdd(&s_acc[2 * g], a);
+        atomicAdd(&s_acc[2 * g + 1], q);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int g = (col * 8 + k) / cpg;
+            atomicAdd(&s_acc[2 * g], s[k]);
+            atomicAdd(&s_acc[2 * g + 1], ss[k]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < GN_GROUPS * 2)
+        atomicAdd(&stats[(int64_t)b * GN_GROUPS * 2 + threadIdx.x], (double)s_acc[threadIdx.x]);
+}
+
+__device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ stats, int b, int g, double n, float eps,
+                                             float& mean, float& rstd) {
+    const double s = stats[((int64_t)b * GN_GROUPS + g) * 2], q = stats[((int64_t)b * GN_GROUPS + g) * 2 + 1];
+    const double m = s / n;
+    double var = q / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// y = [swish]( (x - mean) * rstd * gamma + beta )  -> bf16
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ stats,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              bf16* __restrict__ y, int64_t HW, int C, int vc, int rows,
+                                                              int64_t ppb, float eps) {
+    extern __shared__ float s_ab[];   // scale[C], shift[C]
+    const int b = blockIdx.y;
+    const int cpg = C / GN_GROUPS;
+    const double n = (double)HW * cpg;
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+        float mean, rstd;
+        gn_mean_rstd(stats, b, c / cpg, n, eps, mean, rstd);
+        const float sc = rstd * gamma[c];
+        s_ab[c] = sc;
+        s_ab[C + c] = beta[c] - mean * sc;
+    }
+    __syncthreads();
+    const int col = threadIdx.x % vc, row = threadIdx.x / vc;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = s_ab[col * 8 + k]; sh[k] = s_ab[C + col * 8 + k]; }
+    const int64_t p0 = (int64_t)blockIdx.x * ppb;
+    const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
+    const int64_t off = (int64_t)b * HW * C + col * 8;
+    for (int64_t p = p0 + row; p < p1; p += rows) {
+        float f[8];
+        unpack_bf16x8(ld_stream16(x + off + p * C), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float v = f[k] * sc[k] + sh[k];
+            f[k] = SILU ? v * sigmoidf_fast(v) : v;
+        }
+        st_stream16(y + off + p * C, pack_bf16x8(f));
+    }
+}
+
+// Backward, pass 1.  dy = da * swish'(y).  Per channel: A_c = sum dy, B_c = sum dy * xhat.
+//   dbeta_c += A_c ; dgamma_c += B_c ; gsum[b][g] += {sum_c gamma_c A_c, sum_c gamma_c B_c}
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(
+    const bf16* __restrict__ da, const bf16* __restrict__ x, const double* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ gsum,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t HW, int C, int vc, int rows, int64_t ppb, float eps) {
+    extern __shared__ float s_mem[];   // mean[C] rstd[C] accA[C] accB[C]
+    float* s_mean = s_mem; float* s_rstd = s_mem + C; float* s_A = s_mem + 2 * C; float* s_B = s_mem + 3 * C;
+    const int b = blockIdx.y;
+    const int cpg = C / GN_GROUPS;
+    const double n = (double)HW * cpg;
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+        gn_mean_rstd(stats, b, c / cpg, n, eps, s_mean[c], s_rstd[c]);
+        s_A[c] = 0.f; s_B[c] = 0.f;
+    }
+    __syncthreads();
+    const int col = threadIdx.x % vc, row = threadIdx.x / vc;
+    float mean[8], rstd[8], gm[8], bt[8], A[8], Bv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = col * 8 + k;
+        mean[k] = s_mean[c]; rstd[k] = s_rstd[c]; gm[k] = gamma[c]; bt[k] = beta[c]; A[k] = 0.f; Bv[k] = 0.f;
+    }
+    const int64_t p0 = (int64_t)blockIdx.x * ppb;
+    const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
+    const int64_t off = (int64_t)b * HW * C + col * 8;
+    for (int64_t p = p0 + row; p < p1; p += rows) {
+        float fx[8], fd[8];
+        unpack_bf16x8(ld_stream16(x + off + p * C), fx);
+        unpack_bf16x8(ld_stream16(da + off + p * C), fd);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float xh = (fx[k] - mean[k]) * rstd[k];
+            float dy = fd[k];
+            if (SILU) {
+                const float yv = xh * gm[k] + bt[k];
+                const float sg = sigmoidf_fast(yv);
+                dy *= sg * (1.f + yv * (1.f - sg));
+            }
+            A[k] += dy; Bv[k] += dy * xh;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&s_A[col * 8 + k], A[k]); atomicAdd(&s_B[col * 8 + k], Bv[k]); }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+        atomicAdd(&dbeta[c], s_A[c]);
+        atomicAdd(&dgamma[c], s_B[c]);
+    }
+    if (threadIdx.x < GN_GROUPS) {
+        const int g = threadIdx.x;
+        float a = 0.f, q = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += gamma[c] * s_A[c]; q += gamma[c] * s_B[c]; }
+        atomicAdd(&gsum[((int64_t)b * GN_GROUPS + g) * 2], (double)a);
+        atomicAdd(&gsum[((int64_t)b * GN_GROUPS + g) * 2 + 1], (double)q);
+    }
+}
+
+// Backward, pass 2.  dx = rstd * (gamma*dy - (S1 + xhat*S2)/n) [+ dres]
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
+    const bf16* __restrict__ da, const bf16* __restrict__ x, const double* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ gsum,
+    const bf16* __restrict__ dres, bf16* __restrict__ dx, int64_t HW, int C, int vc, int rows, int64_t ppb, float eps) {
+    extern __shared__ float s_mem[];   // mean[C] rstd[C] m1[C] m2[C]
+    float* s_mean = s_mem; float* s_rstd = s_mem + C; float* s_m1 = s_mem + 2 * C; float* s_m2 = s_mem + 3 * C;
+    const int b = blockIdx.y;
+    const int cpg = C / GN_GROUPS;
+    const double n = (double)HW * cpg;
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+        const int g = c / cpg;
+        gn_mean_rstd(stats, b, g, n, eps, s_mean[c], s_rstd[c]);
+        s_m1[c] = (float)(gsum[((int64_t)b * GN_GROUPS + g) * 2] / n);
+        s_m2[c] = (float)(gsum[((int64_t)b * GN_GROUPS + g) * 2 + 1] / n);
+    }
+    __syncthreads();
+    const int col = threadIdx.x % vc, row = threadIdx.x / vc;
+    float mean[8], rstd[8], gm[8], bt[8], m1[8], m2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = col * 8 + k;
+        mean[k] = s_mean[c]; rstd[k] = s_rstd[c]; gm[k] = gamma[c]; bt[k] = beta[c]; m1[k] = s_m1[c]; m2[k] = s_m2[c];
+    }
+    const int64_t p0 = (int64_t)blockIdx.x * ppb;
+    const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
+    const int64_t off = (int64_t)b * HW * C + col * 8;
+    for (int64_t p = p0 + row; p < p1; p += rows) {
+        float fx[8], fd[8], fr[8];
+        unpack_bf16x8(ld_stream16(x + off + p * C), fx);
+        unpack_bf16x8(ld_stream16(da + off + p * C), fd);
+        if (dres) unpack_bf16x8(ld_stream16(dres + off + p * C), fr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float xh = (fx[k] - mean[k]) * rstd[k];
+            float dy = fd[k];
+            if (SILU) {
+                const float yv = xh * gm[k] + bt[k];
+                const float sg = sigmoidf_fast(yv);
+                dy *= sg * (1.f + yv * (1.f - sg));
+            }
+            float v = rstd[k] * (gm[k] * dy - m1[k] - xh * m2[k]);
+            if (dres) v += fr[k];
+            fx[k] = v;
+        }
+        st_stream16(dx + off + p * C, pack_bf16x8(fx));
+    }
+}
+
+DMVAE_API int dmvae_gn_stats(const void* x, double* stats, int64_t B, int64_t HW, int C, void* stream) {
+    DMVAE_CHECK_ARG(x && stats, "gn_stats: null pointer");
+    DMVAE_CHECK_ARG(B >= 0 && HW >= 0, "gn_stats: negative size");
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0, "gn_stats: x must be 16-byte aligned");
+    GnGeom g;
+    int rc = gn_geom(C, &g, "gn_stats");
+    if (rc) return rc;
+    if (B * HW == 0) return DMVAE_OK;
+    dim3 grid; int64_t ppb;
+    gn_grid(B, HW, g.rows, &grid, &ppb);
+    gn_stats_kernel<<<grid, GN_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, stats, HW, C, g.vc, g.rows, ppb);
+    DMVAE_CHECK_LAUNCH("gn_stats_kernel");
+    return DMVAE_OK;
+}
+
+DMVAE_API int dmvae_gn_apply(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
+                             int64_t B, int64_t HW, int C, float eps, int silu, void* stream) {
+    DMVAE_CHECK_ARG(x && stats && gamma && beta && y, "gn_apply: null pointer");
+    DMVAE_CHECK_ARG(B >= 0 && HW >= 0, "gn_apply: negative size");
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "gn_apply: buffers must be 16-byte aligned");
+    GnGeom g;
+    int rc = gn_geom(C, &g, "gn_apply");
+    if (rc) return rc;
+    if (B * HW == 0) return DMVAE_OK;
+    dim3 grid; int64_t ppb;
+    gn_grid(B, HW, g.rows, &grid, &ppb);
+    const size_t smem = (size_t)2 * C * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (silu) gn_apply_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, g.vc, g.rows, ppb, eps);
+    else      gn_apply_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, g.vc, g.rows, ppb, eps);
+    DMVAE_CHECK_LAUNCH("gn_apply_kernel");
+    return DMVAE_OK;
+}
+
+// gsum (fp64 [B][32][2]), dgamma, dbeta (fp32 [C]) are accumulated into: caller zero-initialises.
+DMVAE_API int dmvae_gn_bwd(const void* da, const void* x, const double* stats, const float* gamma, const float* beta,
+                           double* gsum, float* dgamma, float* dbeta, const void* dres, void* dx, int64_t B,
+                           int64_t HW, int C, float eps, int silu, void* stream) {
+    DMVAE_CHECK_ARG(da && x && stats && gamma && beta && gsum && dgamma && dbeta && dx, "gn_bwd: null pointer");
+    DMVAE_CHECK_ARG(B >= 0 && HW >= 0, "gn_bwd: negative size");
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)da & 15) == 0 && ((uintptr_t)dx & 15) == 0 &&
+                    ((uintptr_t)dres & 15) == 0, "gn_bwd: buffers must be 16-byte aligned");
+    GnGeom g;
+    int rc = gn_geom(C, &g, "gn_bwd");
+    if (rc) return rc;
+    if (B * HW == 0) return DMVAE_OK;
+    dim3 grid; int64_t ppb;
+    gn_grid(B, HW, g.rows, &grid, &ppb);
+    const size_t smem = (size_t)4 * C * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (silu) {
+        gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
+        DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");
+        gn_bwd_apply_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, HW, C, g.vc, g.rows, ppb, eps);
+    } else {
+        gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
+        DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");
+        gn_bwd_apply_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, HW, C, g.vc, g.rows, ppb, eps);
+    }
+    DMVAE_CHECK_LAUNCH("gn_bwd_apply_kernel");
+    return DMVAE_OK;
+}

@@ -1,0 +1,204 @@
+// Layout and small data-movement kernels around the conv tiles.
+//   * NCHW <-> channels-last transposes with dtype conversion (module boundary: the reference's modules take and
+//     return NCHW tensors, models/flux_ae.py:239-269; inside the library everything is [b][pixel][c] bf16)
+//   * nearest-neighbour 2x upsample fwd/bwd               (models/flux_ae.py:103-104, F.interpolate(scale_factor=2, "nearest"))
+//   * zero pad (0,1,0,1) helper is not needed: the stride-2 conv handles the bottom/right pad by bounds checks (:91-95)
+//   * weight packing: fp32 [Cout][Cin][kh][kw] master weights -> bf16 tap-major GEMM operands
+//   * bf16 elementwise add (gradient fan-in of residual branches, :82 / :52)
+#include "common.cuh"
+
+// src[b][R][C] (TI)  ->  dst[b][C][R] (TO), tiled through shared memory so both sides are coalesced
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) transpose_rc_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int64_t R, int64_t C) {
+    __shared__ float tile[32][33];
+    const int64_t b = blockIdx.z;
+    const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const TI* s = src + b * R * C;
+    TO* d = dst + b * R * C;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int64_t r = r0 + ty + i, c = c0 + tx;
+        if (r < R && c < C) tile[ty + i][tx] = ld_as_float(s, r * C + c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int64_t c = c0 + ty + i, r = r0 + tx;
+        if (r < R && c < C) st_from_float(d, c * R + r, tile[tx][ty + i]);
+    }
+}
+
+template <typename TI, typename TO>
+static int launch_transpose(const void* src, void* dst, int64_t B, int64_t R, int64_t C, cudaStream_t st, const char* who) {
+    if (B * R * C == 0) return DMVAE_OK;
+    if (B > 65535 || ceil_div64(C, 32) > 65535) return dmvae_set_error(DMVAE_EUNSUPPORTED, "%s: grid too large", who);
+    dim3 grid((unsigned)ceil_div64(R, 32), (unsigned)ceil_div64(C, 32), (unsigned)B);
+    transpose_rc_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)src, (TO*)dst, R, C);
+    DMVAE_CHECK_LAUNCH(who);
+    return DMVAE_OK;
+}
+
+// NCHW (src_dtype) -> channels-last bf16.   [b][C][HW] -> [b][HW][C]
+DMVAE_API int dmvae_nchw_to_nhwc(const void* src, void* dst, int64_t B, int C, int64_t HW, int src_dtype, void* stream) {
+    DMVAE_CHECK_ARG(src && dst, "nchw_to_nhwc: null pointer");
+    DMVAE_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "nchw_to_nhwc: negative size");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == DMVAE_F32) return launch_transpose<float, bf16>(src, dst, B, C, HW, st, "nchw_to_nhwc");
+    if (src_dtype == DMVAE_BF16) return launch_transpose<bf16, bf16>(src, dst, B, C, HW, st, "nchw_to_nhwc");
+    return dmvae_set_error(DMVAE_EINVAL, "nchw_to_nhwc: bad dtype %d", src_dtype);
+}
+
+// channels-last bf16 -> NCHW (dst_dtype).   [b][HW][C] -> [b][C][HW]
+DMVAE_API int dmvae_nhwc_to_nchw(const void* src, void* dst, int64_t B, int C, int64_t HW, int dst_dtype, void* stream) {
+    DMVAE_CHECK_ARG(src && dst, "nhwc_to_nchw: null pointer");
+    DMVAE_CHECK_ARG(B >= 0 && C >= 0 && HW >= 0, "nhwc_to_nchw: negative size");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst_dtype == DMVAE_F32) return launch_transpose<bf16, float>(src, dst, B, HW, C, st, "nhwc_to_nchw");
+    if (dst_dtype == DMVAE_BF16) return launch_transpose<bf16, bf16>(src, dst, B, HW, C, st, "nhwc_to_nchw");
+    return dmvae_set_error(DMVAE_EINVAL, "nhwc_to_nchw: bad dtype %d", dst_dtype);
+}
+
+// ---- nearest 2x upsample, channels-last bf16, C % 8 == 0 -------------------------------------------------
+__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                             int64_t B, int H, int W, int vc) {
+    // one thread per output 16-byte vector
+    const int64_t n = B * (2 * H) * (2 * W) * vc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vc);
+        int64_t p = i / vc;
+        const int ow = (int)(p % (2 * W)); p /= (2 * W);
+        const int oh = (int)(p % (2 * H));
+        const int64_t b = p / (2 * H);
+        y[i] = x[((b * H + (oh >> 1)) * W + (ow >> 1)) * vc + v];
+    }
+}
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                                                             int64_t B, int H, int W, int vc) {
+    const int64_t n = B * H * W * vc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vc);
+        int64_t p = i / vc;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int64_t b = p / H;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw) {
+                float f[8];
+                unpack_bf16x8(ld_stream16(&dy[((b * 2 * H + 2 * h + dh) * 2 * W + 2 * w + dw) * vc + v]), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += f[k];
+            }
+        dx[i] = pack_bf16x8(acc);
+    }
+}
+
+static unsigned ew_grid(int64_t n) {
+    int64_t g = ceil_div64(n, 256);
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+DMVAE_API int dmvae_upsample2x_fwd(const void* x, void* y, int64_t B, int H, int W, int C, void* stream) {
+    DMVAE_CHECK_ARG(x && y, "upsample2x_fwd: null pointer");
+    DMVAE_CHECK_ARG(C % 8 == 0, "upsample2x_fwd: C must be a multiple of 8 (got %d)", C);
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "upsample2x_fwd: buffers must be 16-byte aligned");
+    const int64_t n = B * 4 * H * W * (C / 8);
+    if (n == 0) return DMVAE_OK;
+    upsample2x_fwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, B, H, W, C / 8);
+    DMVAE_CHECK_LAUNCH("upsample2x_fwd_kernel");
+    return DMVAE_OK;
+}
+
+// dy: [B][2H][2W][C] -> dx: [B][H][W][C] (sum of the 4 replicas, fp32 accumulate)
+DMVAE_API int dmvae_upsample2x_bwd(const void* dy, void* dx, int64_t B, int H, int W, int C, void* stream) {
+    DMVAE_CHECK_ARG(dy && dx, "upsample2x_bwd: null pointer");
+    DMVAE_CHECK_ARG(C % 8 == 0, "upsample2x_bwd: C must be a multiple of 8 (got %d)", C);
+    DMVAE_CHECK_ARG(((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0, "upsample2x_bwd: buffers must be 16-byte aligned");
+    const int64_t n = B * H * W * (C / 8);
+    if (n == 0) return DMVAE_OK;
+    upsample2x_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (uint4*)dx, B, H, W, C / 8);
+    DMVAE_CHECK_LAUNCH("upsample2x_bwd_kernel");
+    return DMVAE_OK;
+}
+
+// ---- bf16 add ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                       bf16* __restrict__ o, int64_t n) {
+    const int64_t nv = n >> 3;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        float fa[8], fb[8];
+        unpack_bf16x8(ld_stream16(a + 8 * i), fa);
+        unpack_bf16x8(ld_stream16(b + 8 * i), fb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+        st_stream16(o + 8 * i, pack_bf16x8(fa));
+    }
+    for (int64_t i = (nv << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        o[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+
+DMVAE_API int dmvae_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
+    DMVAE_CHECK_ARG(a && b && out, "add_bf16: null pointer");
+    DMVAE_CHECK_ARG(n >= 0, "add_bf16: negative size");
+    DMVAE_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)out & 15) == 0, "add_bf16: buffers must be 16-byte aligned");
+    if (n == 0) return DMVAE_OK;
+    add_bf16_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
+    DMVAE_CHECK_LAUNCH("add_bf16_kernel");
+    return DMVAE_OK;
+}
+
+// ---- weight packing ------------------------------------------------------------------------------------------
+// w[co][ci][kh][kw] fp32  ->  wf[tap][co][ci] bf16  (forward operand, K = ci contiguous)
+//                         ->  wd[tap'][ci][co] bf16 (dgrad operand: tap' = flipped tap, K = co contiguous)
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wf,
+                                                           bf16* __restrict__ wd, int Cout, int Cin, int KH, int KW) {
+    const int64_t n = (int64_t)Cout * Cin * KH * KW;
+    const int taps = KH * KW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        // i enumerates the *packed forward* layout so writes to wf are coalesced
+        const int ci = (int)(i % Cin);
+        const int co = (int)((i / Cin) % Cout);
+        const int tap = (int)(i / ((int64_t)Cin * Cout));
+        const float v = w[((int64_t)co * Cin + ci) * taps + tap];
+        const bf16 h = __float2bfloat16_rn(v);
+        if (wf) wf[i] = h;
+        if (wd) wd[((int64_t)(taps - 1 - tap) * Cin + ci) * Cout + co] = h;
+    }
+}
+
+DMVAE_API int dmvae_pack_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KH, int KW, void* stream) {
+    DMVAE_CHECK_ARG(w && (w_fwd || w_dgrad), "pack_weights: null pointer");
+    DMVAE_CHECK_ARG(Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "pack_weights: bad shape");
+    const int64_t n = (int64_t)Cout * Cin * KH * KW;
+    pack_weights_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)w_fwd, (bf16*)w_dgrad, Cout, Cin, KH, KW);
+    DMVAE_CHECK_LAUNCH("pack_weights_kernel");
+    return DMVAE_OK;
+}
+
+// tap-major wgrad scratch [tap][Cout][Cin] -> state_dict layout dw[co][ci][tap] (accumulate=1: +=)
+__global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restrict__ dwp, float* __restrict__ dw,
+                                                           int Cout, int Cin, int taps, int accumulate) {
+    const int64_t n = (int64_t)Cout * Cin * taps;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        // i enumerates the destination so the writes are coalesced; reads of a 3x3 filter hit 9 planes
+        const int tap = (int)(i % taps);
+        const int64_t cc = i / taps;                       // co*Cin + ci
+        const float v = dwp[(int64_t)tap * Cout * Cin + cc];
+        dw[i] = accumulate ? dw[i] + v : v;
+    }
+}
+
+DMVAE_API int dmvae_wgrad_unpack(const float* dw_tap_major, float* dw, int Cout, int Cin, int taps, int accumulate, void* stream) {
+    DMVAE_CHECK_ARG(dw_tap_major && dw, "wgrad_unpack: null pointer");
+    DMVAE_CHECK_ARG(Cout > 0 && Cin > 0 && taps > 0, "wgrad_unpack: bad shape");
+    const int64_t n = (int64_t)Cout * Cin * taps;
+    wgrad_unpack_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dw_tap_major, dw, Cout, Cin, taps, accumulate);
+    DMVAE_CHECK_LAUNCH("wgrad_unpack_kernel");
+    return DMVAE_OK;
+}

@@ -1,0 +1,156 @@
+/*
+ * libdmvae_b200.so -- C ABI of the B200-native DMVAE training hot path.
+ *
+ * The reference (sen-ye/dmvae) has no FFI: its hot path is PyTorch nn.Module composition whose arithmetic runs in
+ * cuDNN / ATen library kernels.  Each entry point below replaces one such library call site; the reference
+ * file:line it stands in for is given per function.  Host code (dmvae_b200/*.py) binds these with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch's allocator in practice); the library keeps
+ *     no state except a TMA-descriptor cache keyed by (pointer, shape);
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises with the host inside a call;
+ *   - activations are channels-last bf16:  x[b][h][w][c], c fastest ("NHWC");
+ *   - packed weights are bf16 [tap][Cout][Cin] (see dmvae_pack_weights);
+ *   - reductions are returned through caller-zeroed fp64 accumulators on the device (no host round trip);
+ *   - return value: 0 on success, negative DMVAE_E* otherwise; dmvae_last_error() describes the failure.
+ *   - dtype codes: DMVAE_F32 = 0, DMVAE_BF16 = 1.
+ */
+#ifndef DMVAE_B200_H
+#define DMVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMVAE_OK 0
+#define DMVAE_EINVAL (-1)
+#define DMVAE_ECUDA (-2)
+#define DMVAE_EUNSUPPORTED (-3)
+
+#define DMVAE_F32 0
+#define DMVAE_BF16 1
+
+const char* dmvae_last_error(void);
+int dmvae_abi_version(void);
+/* 0 if the current CUDA device is sm_100 (B200); the host layer refuses to run otherwise. */
+int dmvae_check_device(void);
+
+/* ------------------------------------------------------------------ A3: DMD loss (train_dmd.py:204-230) ---- */
+
+/* xt = t*z + (1-t)*x0 with the reference's per-op rounding.  Replaces ICPlan.plan / compute_mu_t
+ * (diffusion/transport/path.py:114-136) as called from train_dmd.py:210.  z,x0,xt: [B][per_sample]; t: [B]. */
+int dmvae_dmd_mix_xt(const void* z, const void* x0, const void* t, void* xt, int64_t B, int64_t per_sample,
+                     int dtype, void* stream);
+
+/* Fused CFG mix + pred + p_real/p_student + per-sample mean|p_real| normaliser + nan_to_num + 0.5*MSE surrogate
+ * + latent gradient.  Replaces the ~25 ATen kernels of train_dmd.py:214-228 (normalize=1, cfg_scale>1) and the
+ * toy variant toy_example_2d/dmd.py:349-360 (normalize=0, vT_u=vS_u=NULL).
+ *   acc[0] += sum (z - target)^2   (loss = 0.5 * acc[0] / (B*per_sample))
+ *   acc[1] += sum_b ||grad_b||_2   (dmd_gradient_norm = acc[1] / B)
+ *   dz      = grad_scale * (z - target) / (B*per_sample)       stored as dz_dtype */
+int dmvae_dmd_loss_fwd_bwd(const void* z, const void* xt, const void* t, const void* vT_c, const void* vT_u,
+                           const void* vS_c, const void* vS_u, void* dz, double* acc, int64_t B,
+                           int64_t per_sample, float cfg_scale, int normalize, float grad_scale, int dtype,
+                           int dz_dtype, void* stream);
+
+/* ------------------------------------------------------------------ A4: L1 + L2 (train_dmd.py:234-235) ----- */
+
+/* acc[0] += sum|recon-image| ; acc[1] += sum (recon-image)^2.   Replaces F.l1_loss + F.mse_loss forward. */
+int dmvae_l1l2_fwd(const float* recon, const float* image, double* acc, int64_t n, void* stream);
+/* d_recon = (w_l1*g1*sign(d) + 2*w_l2*g2*d)/n ; g1,g2 device scalars (upstream grads) or NULL (=0 contribution). */
+int dmvae_l1l2_bwd(const float* recon, const float* image, float* d_recon, const float* g1, const float* g2,
+                   int64_t n, float w_l1, float w_l2, void* stream);
+/* single pass: sums as dmvae_l1l2_fwd and d_recon = d(w_l1*L1 + w_l2*L2)/d recon. */
+int dmvae_l1l2_fwd_bwd(const float* recon, const float* image, float* d_recon, double* acc, int64_t n,
+                       float w_l1, float w_l2, void* stream);
+
+/* ------------------------------------------------------------------ A5: LPIPS distance (utils/lpips.py:86-94) */
+
+/* One VGG tap: acc[b] += sum_pixels sum_c w[c] * (f0/(|f0|+1e-10) - f1/(|f1|+1e-10))^2.   Replaces
+ * normalize_tensor (:156), the squared difference (:89), NetLinLayer 1x1 conv (:91,107) and the spatial sum of
+ * spatial_average (:161).  f0,f1: channels-last [B][HW][C]; lin_w: fp32 [C].  faithful=1 applies the bf16
+ * roundings autocast inserts around the 1x1 conv. */
+int dmvae_lpips_dist_fwd(const void* f0, const void* f1, const float* lin_w, double* acc, int64_t B, int64_t HW,
+                         int C, int dtype, int faithful, void* stream);
+/* df1 = scale * (*gout) * d(distance)/d f1   (the reference passes (images, recon): only f1 needs a gradient). */
+int dmvae_lpips_dist_bwd(const void* f0, const void* f1, const float* lin_w, void* df1, const float* gout,
+                         int64_t B, int64_t HW, int C, float scale, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ A8: reparameterize + KL (extension) ---- */
+
+/* h rows = [mu | logvar], each `half` long; z = mu + exp(lv/2)*eps; acc[0] += 0.5*sum(mu^2 + e^lv - 1 - lv).
+ * No reference implementation exists; oracle/dmvae_oracle.py:reparam_kl states the math. */
+int dmvae_reparam_kl_fwd(const void* h, const void* eps, void* z, double* acc, int64_t rows, int64_t half,
+                         int dtype, void* stream);
+int dmvae_reparam_kl_bwd(const void* h, const void* eps, const void* dz, void* dh, const float* g_kl,
+                         float kl_scale, int64_t rows, int64_t half, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ A1a: GroupNorm(32)+swish ---------------- */
+/* models/flux_ae.py:21-22,30,62,64,157,236.  x,y,da,dx: channels-last bf16 [B][HW][C]; stats fp64 [B][32][2]. */
+
+/* stats[b][g] += {sum x, sum x^2}  (caller zeroes). */
+int dmvae_gn_stats(const void* x, double* stats, int64_t B, int64_t HW, int C, void* stream);
+/* y = [swish]((x-mean)*rstd*gamma+beta) rounded to bf16. */
+int dmvae_gn_apply(const void* x, const double* stats, const float* gamma, const float* beta, void* y, int64_t B,
+                   int64_t HW, int C, float eps, int silu, void* stream);
+/* backward of the above: dx (+= dres if given), dgamma/dbeta (fp32 [C], accumulated), gsum = fp64 scratch
+ * [B][32][2] (caller zeroes). */
+int dmvae_gn_bwd(const void* da, const void* x, const double* stats, const float* gamma, const float* beta,
+                 double* gsum, float* dgamma, float* dbeta, const void* dres, void* dx, int64_t B, int64_t HW,
+                 int C, float eps, int silu, void* stream);
+
+/* ------------------------------------------------------------------ A1/A2: convolutions --------------------- */
+
+/* fp32 master weight [Cout][Cin][KH][KW] (the state_dict tensor) -> bf16 GEMM operands:
+ *   w_fwd  [tap][Cout][Cin]            forward / wgrad layout
+ *   w_dgrad[taps-1-tap][Cin][Cout]     data-gradient layout (either may be NULL). */
+int dmvae_pack_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KH, int KW,
+                       void* stream);
+
+/* 1 if the shape runs on the tcgen05 tile (stride 1, 3x3 pad 1 or 1x1, C%8==0, pixel tile divides H,W). */
+int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW);
+
+/* tcgen05 implicit GEMM.  Replaces cuDNN conv forward for nn.Conv2d at models/flux_ae.py:32-35,63,65,67,101,210
+ * and -- fed dY and w_dgrad -- cuDNN's backward-data.   y = conv(x) + bias ; if residual: y = bf16(y) + residual. */
+int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
+                      int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
+
+/* tcgen05 weight gradient (both operands MN-major): dw_tap_major[tap][Cout][Cin] (fp32, caller-zeroed or
+ * accumulated) += sum_pixels dy[p][co] * x[p(+)tap][ci].  Replaces cuDNN backward-filter for the same call sites.
+ * dmvae_wgrad_unpack moves the tap-major scratch into the state_dict layout dw[Cout][Cin][KH][KW]. */
+int dmvae_conv_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW);
+int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_major, int B, int H, int W, int Cin, int Cout,
+                        int KH, int KW, void* stream);
+int dmvae_wgrad_unpack(const float* dw_tap_major, float* dw, int Cout, int Cin, int taps, int accumulate,
+                       void* stream);
+
+/* CUDA-core path for the ragged layers (Cin=32 stem :272-275, Cout=3 head :237, Cin=3 encoder stem :133,
+ * stride-2 Downsample :89-95) and the on-device cross-check of the tensor-core path. */
+int dmvae_conv_direct_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
+                          int B, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
+                          int pad_top, int pad_left, void* stream);
+int dmvae_conv_direct_dgrad_strided(const void* dy, const void* w_packed, void* dx, int B, int H, int W, int Cin,
+                                    int OH, int OW, int Cout, int KH, int KW, int stride, int pad_top,
+                                    int pad_left, void* stream);
+int dmvae_conv_direct_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int OH, int OW,
+                            int Cout, int KH, int KW, int stride, int pad_top, int pad_left, void* stream);
+/* dbias[c] += sum_rows dy[row][c]. */
+int dmvae_bias_grad(const void* dy, float* dbias, int64_t M, int C, void* stream);
+
+/* ------------------------------------------------------------------ A1c / A6: data movement ---------------- */
+
+/* F.interpolate(scale_factor=2, mode="nearest") (models/flux_ae.py:104) and its adjoint, channels-last bf16. */
+int dmvae_upsample2x_fwd(const void* x, void* y, int64_t B, int H, int W, int C, void* stream);
+int dmvae_upsample2x_bwd(const void* dy, void* dx, int64_t B, int H, int W, int C, void* stream);
+/* NCHW (fp32|bf16) <-> channels-last bf16 at the module boundary (models/flux_ae.py:244-245, models/vae.py:97). */
+int dmvae_nchw_to_nhwc(const void* src, void* dst, int64_t B, int C, int64_t HW, int src_dtype, void* stream);
+int dmvae_nhwc_to_nchw(const void* src, void* dst, int64_t B, int C, int64_t HW, int dst_dtype, void* stream);
+/* out = a + b (bf16, fp32 add, one rounding): gradient fan-in of the residual branches (:52, :82). */
+int dmvae_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMVAE_B200_H */
