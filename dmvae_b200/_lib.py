@@ -1,0 +1,115 @@
+"""ctypes binding of libdmvae_b200.so (the C ABI declared in include/dmvae_b200.h).
+
+There is no fallback: if the shared library is missing the import of any compute entry point raises, and a
+compute call on a device that is not sm_100 raises (dmvae_check_device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdmvae_b200.so")
+
+F32, BF16 = 0, 1
+_p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argtypes  (every function returns int except dmvae_last_error)
+SIGNATURES = {
+    "dmvae_abi_version": [],
+    "dmvae_check_device": [],
+    "dmvae_dmd_mix_xt": [_p, _p, _p, _p, _i64, _i64, _i, _p],
+    "dmvae_dmd_loss_fwd_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _i, _f, _i, _i, _p],
+    "dmvae_l1l2_fwd": [_p, _p, _p, _i64, _p],
+    "dmvae_l1l2_bwd": [_p, _p, _p, _p, _p, _i64, _f, _f, _p],
+    "dmvae_l1l2_fwd_bwd": [_p, _p, _p, _p, _i64, _f, _f, _p],
+    "dmvae_lpips_dist_fwd": [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _p],
+    "dmvae_lpips_dist_bwd": [_p, _p, _p, _p, _p, _i64, _i64, _i, _f, _i, _p],
+    "dmvae_reparam_kl_fwd": [_p, _p, _p, _p, _i64, _i64, _i, _p],
+    "dmvae_reparam_kl_bwd": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p],
+    "dmvae_gn_stats": [_p, _p, _i64, _i64, _i, _p],
+    "dmvae_gn_apply": [_p, _p, _p, _p, _p, _i64, _i64, _i, _f, _i, _p],
+    "dmvae_gn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _i, _p],
+    "dmvae_pack_weights": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "dmvae_conv_tc_supported": [_i] * 7,
+    "dmvae_conv_tc_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "dmvae_conv_tc_wgrad_supported": [_i] * 7,
+    "dmvae_conv_tc_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "dmvae_wgrad_unpack": [_p, _p, _i, _i, _i, _i, _p],
+    "dmvae_conv_direct_fwd": [_p, _p, _p, _p, _p] + [_i] * 12 + [_p],
+    "dmvae_conv_direct_dgrad_strided": [_p, _p, _p] + [_i] * 12 + [_p],
+    "dmvae_conv_direct_wgrad": [_p, _p, _p] + [_i] * 12 + [_p],
+    "dmvae_bias_grad": [_p, _p, _i64, _i, _p],
+    "dmvae_upsample2x_fwd": [_p, _p, _i64, _i, _i, _i, _p],
+    "dmvae_upsample2x_bwd": [_p, _p, _i64, _i, _i, _i, _p],
+    "dmvae_nchw_to_nhwc": [_p, _p, _i64, _i, _i64, _i, _p],
+    "dmvae_nhwc_to_nchw": [_p, _p, _i64, _i, _i64, _i, _p],
+    "dmvae_add_bf16": [_p, _p, _p, _i64, _p],
+}
+
+_lib: Optional[C.CDLL] = None
+_device_ok = False
+
+
+class DmvaeError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (CPU-safe: touches no device)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DmvaeError(
+                f"{LIB_PATH} is missing: build it with `python -m dmvae_b200.build` (nvcc, sm_100a). "
+                "dmvae_b200 has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.dmvae_last_error.restype = C.c_char_p
+        lib.dmvae_last_error.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise DmvaeError(f"unsupported dtype {t.dtype} (float32 / bfloat16 only)")
+
+
+def call(name: str, *args) -> None:
+    """Invoke a compute entry point on the current CUDA stream; raises DmvaeError on failure."""
+    global _device_ok
+    lib = load()
+    if not _device_ok:
+        if not torch.cuda.is_available():
+            raise DmvaeError("dmvae_b200 requires a CUDA device (sm_100a); no CPU fallback exists")
+        if lib.dmvae_check_device() != 0:
+            raise DmvaeError(lib.dmvae_last_error().decode())
+        _device_ok = True
+    rc = getattr(lib, name)(*args, _stream())
+    if rc != 0:
+        raise DmvaeError(f"{name} failed ({rc}): {lib.dmvae_last_error().decode()}")
+
+
+def query(name: str, *args) -> int:
+    """Pure host-side predicate (no device work)."""
+    return getattr(load(), name)(*args)

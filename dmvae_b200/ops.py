@@ -1,0 +1,285 @@
+"""Host-side operators over libdmvae_b200.so: raw kernel wrappers and torch.autograd.Functions.
+
+Activations inside the library are channels-last bf16 tensors of shape (B, H, W, C).  Parameters stay the
+reference's fp32 ``nn.Parameter``s in state_dict layout; the bf16 tap-major GEMM operands are a derived cache
+(``WeightPack``) refreshed when the parameter's version counter moves (optimizer.step / load_state_dict).
+
+Every Function here honours: retain_graph=True with repeated partial ``autograd.grad`` calls (saved tensors are
+never written in place -- the adaptive-GAN-weight code of train_dmd.py:248-251 relies on it), ``no_grad`` /
+``inference_mode`` (nothing is saved), and DDP / clip_grad_norm_ / AdamW on the unmodified parameters.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, call, ptr, query
+
+GN_EPS = 1e-6
+
+
+def _chk_nhwc(x: torch.Tensor, name: str) -> torch.Tensor:
+    if x.dtype != torch.bfloat16 or x.ndim != 4:
+        raise _lib.DmvaeError(f"{name}: expected a (B,H,W,C) bfloat16 tensor, got {tuple(x.shape)} {x.dtype}")
+    if not x.is_cuda:
+        raise _lib.DmvaeError(f"{name}: tensor is on {x.device}; dmvae_b200 has no CPU path")
+    return x if x.is_contiguous() else x.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ weights
+class WeightPack:
+    """bf16 GEMM operands derived from one fp32 conv weight (Cout, Cin, KH, KW)."""
+
+    __slots__ = ("version", "data_ptr", "w_fwd", "w_dgrad")
+
+    def __init__(self):
+        self.version = -1
+        self.data_ptr = 0
+        self.w_fwd = None
+        self.w_dgrad = None
+
+    def get(self, weight: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        v = weight._version
+        if self.w_fwd is None or v != self.version or weight.data_ptr() != self.data_ptr or self.w_fwd.device != weight.device:
+            w = weight.detach()
+            if w.dtype != torch.float32:
+                w = w.float()
+            w = w.contiguous()
+            cout, cin, kh, kw = w.shape
+            # fresh tensors on every repack: graphs that saved the old operands keep valid data
+            wf = torch.empty((kh * kw, cout, cin), dtype=torch.bfloat16, device=w.device)
+            wd = torch.empty((kh * kw, cin, cout), dtype=torch.bfloat16, device=w.device)
+            call("dmvae_pack_weights", ptr(w), ptr(wf), ptr(wd), cout, cin, kh, kw)
+            self.w_fwd, self.w_dgrad, self.version, self.data_ptr = wf, wd, v, weight.data_ptr()
+        return self.w_fwd, self.w_dgrad
+
+
+# ------------------------------------------------------------------------------------------------ raw kernels
+def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+                     kh: int, kw: int, stride: int = 1, pad_tl: Tuple[int, int] = (1, 1),
+                     out_hw: Optional[Tuple[int, int]] = None, force_direct: bool = False) -> torch.Tensor:
+    """y = conv(x, w_packed[tap][Cout][Cin]) + bias (+ residual).  Picks the tcgen05 tile when the shape allows."""
+    B, H, W, cin = x.shape
+    taps, cout, cin_w = w_packed.shape
+    assert taps == kh * kw and cin_w == cin, (w_packed.shape, x.shape, kh, kw)
+    pt, pl = pad_tl
+    if out_hw is None:
+        out_hw = ((H + 2 * pt - kh) // stride + 1, (W + 2 * pl - kw) // stride + 1)
+    OH, OW = out_hw
+    y = torch.empty((B, OH, OW, cout), dtype=torch.bfloat16, device=x.device)
+    if bias is not None and bias.dtype != torch.float32:
+        bias = bias.float()
+    same = stride == 1 and OH == H and OW == W and pt == (kh - 1) // 2 and pl == (kw - 1) // 2
+    if same and not force_direct and query("dmvae_conv_tc_supported", B, H, W, cin, cout, kh, kw):
+        call("dmvae_conv_tc_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, kh, kw)
+    else:
+        call("dmvae_conv_direct_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, OH, OW, cout,
+             kh, kw, stride, pt, pl)
+    return y
+
+
+def conv_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, stride: int = 1, pad_tl: Tuple[int, int] = (1, 1),
+                   force_direct: bool = False) -> torch.Tensor:
+    """dw (Cout, Cin, KH, KW) fp32 = sum_pixels dy (x) x."""
+    B, H, W, cin = x.shape
+    _, OH, OW, cout = dy.shape
+    pt, pl = pad_tl
+    same = stride == 1 and OH == H and OW == W and pt == (kh - 1) // 2 and pl == (kw - 1) // 2
+    if same and not force_direct and query("dmvae_conv_tc_wgrad_supported", B, H, W, cin, cout, kh, kw):
+        scratch = torch.zeros((kh * kw, cout, cin), dtype=torch.float32, device=x.device)
+        call("dmvae_conv_tc_wgrad", ptr(x), ptr(dy), ptr(scratch), B, H, W, cin, cout, kh, kw)
+        dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
+        call("dmvae_wgrad_unpack", ptr(scratch), ptr(dw), cout, cin, kh * kw, 0)
+        return dw
+    dw = torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
+    call("dmvae_conv_direct_wgrad", ptr(x), ptr(dy), ptr(dw), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
+    return dw
+
+
+def conv_dgrad_raw(dy: torch.Tensor, w_fwd: torch.Tensor, w_dgrad: torch.Tensor, in_hw: Tuple[int, int], kh: int, kw: int,
+                   stride: int = 1, pad_tl: Tuple[int, int] = (1, 1), force_direct: bool = False) -> torch.Tensor:
+    B, OH, OW, cout = dy.shape
+    H, W = in_hw
+    pt, pl = pad_tl
+    cin = w_fwd.shape[2]
+    if stride == 1 and OH == H and OW == W:
+        # "same" conv: dX = conv(dY, flipped/transposed weights) with the mirrored padding
+        return conv_forward_raw(dy, w_dgrad, None, None, kh, kw, 1, (kh - 1 - pt, kw - 1 - pl), (H, W), force_direct)
+    dx = torch.empty((B, H, W, cin), dtype=torch.bfloat16, device=dy.device)
+    call("dmvae_conv_direct_dgrad_strided", ptr(dy), ptr(w_fwd), ptr(dx), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
+    return dx
+
+
+def bias_grad_raw(dy: torch.Tensor) -> torch.Tensor:
+    c = dy.shape[-1]
+    db = torch.zeros((c,), dtype=torch.float32, device=dy.device)
+    call("dmvae_bias_grad", ptr(dy), ptr(db), dy.numel() // c, c)
+    return db
+
+
+def gn_stats_raw(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, c = x.shape
+    stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
+    call("dmvae_gn_stats", ptr(x), ptr(stats), B, H * W, c)
+    return stats
+
+
+def gn_apply_raw(x, stats, gamma, beta, silu: bool, eps: float = GN_EPS) -> torch.Tensor:
+    B, H, W, c = x.shape
+    y = torch.empty_like(x)
+    call("dmvae_gn_apply", ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(y), B, H * W, c, eps, int(silu))
+    return y
+
+
+def gn_bwd_raw(da, x, stats, gamma, beta, silu: bool, dres=None, eps: float = GN_EPS):
+    B, H, W, c = x.shape
+    gsum = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
+    dgamma = torch.zeros((c,), dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros((c,), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    call("dmvae_gn_bwd", ptr(da), ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(gsum), ptr(dgamma), ptr(dbeta), ptr(dres),
+         ptr(dx), B, H * W, c, eps, int(silu))
+    return dx, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------------ autograd
+class ConvFn(torch.autograd.Function):
+    """nn.Conv2d on channels-last bf16 (models/flux_ae.py:32-35,63,65,67,89,101,133,158,210,237,274)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, pack: WeightPack, stride: int, pad_tl):
+        x = _chk_nhwc(x, "conv")
+        cout, cin, kh, kw = weight.shape
+        w_fwd, w_dgrad = pack.get(weight)
+        if residual is not None:
+            residual = _chk_nhwc(residual, "conv residual")
+        y = conv_forward_raw(x, w_fwd, None if bias is None else bias.detach(), residual, kh, kw, stride, pad_tl)
+        ctx.geom = (kh, kw, stride, pad_tl, x.shape[1:3])
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, w_fwd, w_dgrad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_fwd, w_dgrad = ctx.saved_tensors
+        kh, kw, stride, pad_tl, in_hw = ctx.geom
+        dy = _chk_nhwc(dy, "conv backward")
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_dgrad_raw(dy, w_fwd, w_dgrad, in_hw, kh, kw, stride, pad_tl)
+        if ctx.needs_input_grad[1]:
+            dw = conv_wgrad_raw(x, dy, kh, kw, stride, pad_tl)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = bias_grad_raw(dy)
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = dy
+        return dx, dw, db, dres, None, None, None
+
+
+class GroupNormSiluFn(torch.autograd.Function):
+    """swish(GroupNorm(32, C, eps=1e-6)(x))  /  GroupNorm alone (silu=False)   (models/flux_ae.py:21-22,70-77,38)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, silu: bool):
+        x = _chk_nhwc(x, "group_norm")
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        stats = gn_stats_raw(x)
+        y = gn_apply_raw(x, stats, g, b, silu)
+        ctx.silu = silu
+        ctx.save_for_backward(x, stats, g, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, da):
+        x, stats, g, b = ctx.saved_tensors
+        da = _chk_nhwc(da, "group_norm backward")
+        dx, dgamma, dbeta = gn_bwd_raw(da, x, stats, g, b, ctx.silu)
+        return dx, dgamma, dbeta, None
+
+
+class Upsample2xFn(torch.autograd.Function):
+    """F.interpolate(scale_factor=2, mode='nearest') (models/flux_ae.py:104)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk_nhwc(x, "upsample2x")
+        B, H, W, c = x.shape
+        y = torch.empty((B, 2 * H, 2 * W, c), dtype=x.dtype, device=x.device)
+        call("dmvae_upsample2x_fwd", ptr(x), ptr(y), B, H, W, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _chk_nhwc(dy, "upsample2x backward")
+        B, H2, W2, c = dy.shape
+        dx = torch.empty((B, H2 // 2, W2 // 2, c), dtype=dy.dtype, device=dy.device)
+        call("dmvae_upsample2x_bwd", ptr(dy), ptr(dx), B, H2 // 2, W2 // 2, c)
+        return dx
+
+
+class ToChannelsLastFn(torch.autograd.Function):
+    """(B, C, H, W) fp32|bf16 -> (B, H, W, C) bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        B, c, H, W = x.shape
+        ctx.in_dtype = x.dtype
+        y = torch.empty((B, H, W, c), dtype=torch.bfloat16, device=x.device)
+        call("dmvae_nchw_to_nhwc", ptr(x), ptr(y), B, c, H * W, _lib.dtype_code(x))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _chk_nhwc(dy, "to_channels_last backward")
+        B, H, W, c = dy.shape
+        dx = torch.empty((B, c, H, W), dtype=ctx.in_dtype, device=dy.device)
+        call("dmvae_nhwc_to_nchw", ptr(dy), ptr(dx), B, c, H * W, _lib.dtype_code(dx))
+        return dx
+
+
+class ToNchwFn(torch.autograd.Function):
+    """(B, H, W, C) bf16 -> (B, C, H, W) in out_dtype."""
+
+    @staticmethod
+    def forward(ctx, x, out_dtype):
+        x = _chk_nhwc(x, "to_nchw")
+        B, H, W, c = x.shape
+        y = torch.empty((B, c, H, W), dtype=out_dtype, device=x.device)
+        call("dmvae_nhwc_to_nchw", ptr(x), ptr(y), B, c, H * W, _lib.dtype_code(y))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        dy = dy.contiguous()
+        B, c, H, W = dy.shape
+        dx = torch.empty((B, H, W, c), dtype=torch.bfloat16, device=dy.device)
+        call("dmvae_nchw_to_nhwc", ptr(dy), ptr(dx), B, c, H * W, _lib.dtype_code(dy))
+        return dx, None
+
+
+def conv2d(x, weight, bias, pack: WeightPack, stride: int = 1, pad_tl=(1, 1), residual=None):
+    return ConvFn.apply(x, weight, bias, residual, pack, stride, pad_tl)
+
+
+def group_norm_silu(x, gamma, beta, silu: bool = True):
+    return GroupNormSiluFn.apply(x, gamma, beta, silu)
+
+
+def upsample2x(x):
+    return Upsample2xFn.apply(x)
+
+
+def to_channels_last(x):
+    return ToChannelsLastFn.apply(x)
+
+
+def to_nchw(x, out_dtype=torch.float32):
+    return ToNchwFn.apply(x, out_dtype)

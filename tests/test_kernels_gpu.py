@@ -1,0 +1,296 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle (oracle/dmvae_oracle.py) on seeded inputs.
+
+Tolerances (stated per test): fp32 elementwise chains are compared at 1e-6 relative (only reduction order differs);
+bf16 tensor-core outputs at 2^-8 relative per element (one bf16 ulp) plus an absolute floor scaled by the
+accumulation length; reduced scalars at 1e-3 relative.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dmvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from dmvae_b200 import ops, losses
+    return ops, losses
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def nhwc(x):  # (B,C,H,W) fp32 cpu -> (B,H,W,C) bf16 cuda
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+
+
+def nchw(y):  # (B,H,W,C) cuda -> (B,C,H,W) fp32 cpu
+    return y.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+# ------------------------------------------------------------------------------------------------ A3
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg,normalize", [(5.0, True), (1.0, True), (1.0, False)])
+@pytest.mark.parametrize("shape", [(4, 32, 16, 16), (3, 2, 1, 1), (5, 7, 3, 3)])
+def test_dmd_loss(dtype, cfg, normalize, shape):
+    _, L = _ops()
+    g = torch.Generator().manual_seed(1)
+    z, x0, vTc, vTu, vSc, vSu = (torch.randn(shape, generator=g).to(dtype) for _ in range(6))
+    t = torch.rand(shape[0], generator=g).to(dtype)
+    xt_ref = O.dmd_mix_xt(z, x0, t)
+    xt = L.dmd_mix_xt(z.to(DEV), x0.to(DEV), t.to(DEV))
+    assert torch.equal(xt.cpu(), xt_ref), "xt mix must be bit-exact (elementwise, per-op rounding)"
+    loss_ref, gn_ref, dz_ref = O.dmd_loss(z, xt_ref, t, vTc, vSc, vTu, vSu, cfg, normalize)
+    zc = z.to(DEV).requires_grad_(True)
+    loss, gn = L.dmd_loss(zc, xt, t.to(DEV), vTc.to(DEV), vSc.to(DEV), vTu.to(DEV), vSu.to(DEV), cfg, normalize)
+    loss.backward()
+    # the per-sample mean|p_real| is a reduction: order differs, and in bf16 it is then rounded to 8 bits, so a
+    # 1-ulp flip of the normaliser moves that sample's grad by 2^-8.  fp32: 1e-5.  bf16: 1e-2.
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert abs(loss.item() - loss_ref.item()) <= tol * abs(loss_ref.item()) + 1e-12
+    assert abs(gn.item() - gn_ref.item()) <= tol * abs(gn_ref.item()) + 1e-12
+    assert rel_err(zc.grad.float(), dz_ref) <= tol
+
+
+def test_dmd_nan_to_num_and_empty():
+    _, L = _ops()
+    # sample 0: p_real == 0 everywhere -> normaliser 0 -> 0/0 = NaN -> 0 ; x/0 = inf -> dtype max (train_dmd.py:224)
+    z = torch.zeros(2, 4, 2, 2); xt = torch.zeros_like(z); t = torch.tensor([0.5, 0.5])
+    vT = torch.zeros_like(z); vS = torch.ones_like(z); vS[0, 0] = 0
+    vT[1] = torch.randn(4, 2, 2)
+    loss_ref, gn_ref, dz_ref = O.dmd_loss(z, xt, t, vT, vS, None, None, 1.0, True)
+    zc = z.to(DEV).requires_grad_(True)
+    loss, gn = L.dmd_loss(zc, xt.to(DEV), t.to(DEV), vT.to(DEV), vS.to(DEV), None, None, 1.0, True)
+    loss.backward()
+    assert torch.isfinite(zc.grad).all()
+    assert rel_err(zc.grad, dz_ref) < 1e-5
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    # empty batch
+    e = torch.zeros(0, 4, 2, 2, device=DEV)
+    loss, gn = L.dmd_loss(e, e, torch.zeros(0, device=DEV), e, e)
+    assert loss.item() == 0.0
+
+
+def test_dmd_large_per_sample_uncached():
+    _, L = _ops()
+    g = torch.Generator().manual_seed(3)
+    shape = (2, 16, 32, 32)   # 16384 elements per sample > shared-memory cache
+    z, xt, vT, vS = (torch.randn(shape, generator=g) for _ in range(4))
+    t = torch.rand(2, generator=g)
+    loss_ref, gn_ref, dz_ref = O.dmd_loss(z, xt, t, vT, vS)
+    zc = z.to(DEV).requires_grad_(True)
+    loss, gn = L.dmd_loss(zc, xt.to(DEV), t.to(DEV), vT.to(DEV), vS.to(DEV))
+    loss.backward()
+    assert rel_err(zc.grad, dz_ref) < 1e-5 and abs(loss.item() - loss_ref.item()) < 1e-5 * loss_ref.item()
+
+
+# ------------------------------------------------------------------------------------------------ A4
+@pytest.mark.parametrize("n", [(2, 3, 64, 64), (1, 3, 5, 7), (0, 3, 4, 4)])
+def test_l1l2(n):
+    _, L = _ops()
+    g = torch.Generator().manual_seed(2)
+    r, x = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    if r.numel():
+        r.view(-1)[0] = x.view(-1)[0]            # exact zero difference: sign(0) = 0
+    rc = r.to(DEV).requires_grad_(True)
+    l1, l2 = L.l1_l2_loss(rc, x.to(DEV))
+    if r.numel() == 0:
+        return
+    l1_ref, l2_ref, g_ref = O.l1l2(r, x, 1.0, 0.7)
+    (l1 * 1.0 + l2 * 0.7).backward()
+    assert abs(l1.item() - l1_ref.item()) < 1e-6 * l1_ref.item()
+    assert abs(l2.item() - l2_ref.item()) < 1e-6 * l2_ref.item()
+    assert rel_err(rc.grad, g_ref) < 1e-6
+    a, b, d = L.l1l2_fused(r.to(DEV), x.to(DEV), 1.0, 0.7)
+    assert rel_err(d, g_ref) < 1e-6 and abs(a.item() - l1_ref.item()) < 1e-6 * l1_ref.item()
+
+
+# ------------------------------------------------------------------------------------------------ A5
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c,hw", [(64, 24), (128, 12), (256, 6), (512, 3)])
+def test_lpips_distance(dtype, c, hw):
+    _, L = _ops()
+    g = torch.Generator().manual_seed(c)
+    f0 = torch.relu(torch.randn(2, c, hw, hw, generator=g)).to(dtype)
+    f1 = torch.relu(torch.randn(2, c, hw, hw, generator=g)).to(dtype)
+    w = torch.rand(c, generator=g)
+    f1r = f1.float().requires_grad_(True)
+    ref = O.lpips_distance([f0], [f1r], [w])
+    ref.backward()
+    f1c = f1.to(DEV).requires_grad_(True)
+    d = L.lpips_tap_distance(f0.to(DEV), f1c, w.to(DEV)).mean()
+    d.backward()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2      # bf16: the gradient is rounded to bf16 at the store
+    assert abs(d.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel_err(f1c.grad.float(), f1r.grad) < tol
+
+
+def test_lpips_distance_faithful_bf16():
+    _, L = _ops()
+    g = torch.Generator().manual_seed(5)
+    f0 = torch.relu(torch.randn(2, 64, 8, 8, generator=g)).bfloat16()
+    f1 = torch.relu(torch.randn(2, 64, 8, 8, generator=g)).bfloat16()
+    w = torch.rand(64, generator=g)
+    ref = O.lpips_distance([f0], [f1], [w], faithful=True)
+    d = L.lpips_tap_distance(f0.to(DEV), f1.to(DEV), w.to(DEV), faithful=True)
+    d = O.r16(O.r16(d.cpu()).mean())
+    assert abs(d.item() - ref.item()) <= 2 ** -7 * abs(ref.item())   # two bf16 ulps on the bf16 tail
+
+
+# ------------------------------------------------------------------------------------------------ A8
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_reparam_kl(dtype):
+    _, L = _ops()
+    g = torch.Generator().manual_seed(4)
+    h = (torch.randn(3, 8, 4, 4, generator=g) * 0.5).to(dtype)
+    eps = torch.randn(3, 4, 4, 4, generator=g).to(dtype)
+    hr = h.float().requires_grad_(True)
+    mu, lv = hr.chunk(2, dim=1)
+    z_ref, kl_ref = O.reparam_kl(mu, lv, eps)
+    (z_ref.sum() * 0.3 + kl_ref * 0.01).backward()
+    hc = h.to(DEV).requires_grad_(True)
+    z, kl = L.reparam_kl(hc, eps.to(DEV), channel_dim=1)
+    (z.float().sum() * 0.3 + kl * 0.01).backward()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(z.float(), z_ref) < tol
+    assert abs(kl.item() - kl_ref.item()) < 1e-4 * abs(kl_ref.item())
+    assert rel_err(hc.grad.float(), hr.grad) < tol
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm
+@pytest.mark.parametrize("c,h,w", [(32, 8, 8), (128, 16, 8), (256, 4, 12), (512, 8, 8)])
+@pytest.mark.parametrize("silu", [True, False])
+def test_group_norm_silu(c, h, w, silu):
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(c + h)
+    x = O.r16(torch.randn(2, c, h, w, generator=g) * 2 + 0.5)
+    gamma = 1 + 0.2 * torch.randn(c, generator=g)
+    beta = 0.1 * torch.randn(c, generator=g)
+    da = O.r16(torch.randn(2, c, h, w, generator=g))
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y_ref = O.group_norm({"n.weight": gr, "n.bias": br}, "n", xr, silu)
+    y_ref.backward(da)
+    xc = nhwc(x).requires_grad_(True)
+    gc, bc = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    y = ops.group_norm_silu(xc, gc, bc, silu)
+    y.backward(nhwc(da))
+    # outputs are bf16: one ulp = 2^-8 relative; norm-wise error is well below that
+    assert rel_err(nchw(y), y_ref.detach()) < 4e-3
+    assert rel_err(nchw(xc.grad), xr.grad) < 6e-3
+    assert rel_err(gc.grad, gr.grad) < 2e-3 and rel_err(bc.grad, br.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def test_layout_roundtrip_and_upsample():
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(7)
+    x = O.r16(torch.randn(2, 40, 6, 10, generator=g))
+    xl = ops.to_channels_last(x.to(DEV))
+    assert torch.equal(nchw(xl), x)                                   # pure transpose: bit-exact
+    back = ops.to_nchw(xl, torch.float32)
+    assert torch.equal(back.cpu(), x)
+    up = ops.upsample2x(xl)
+    assert torch.equal(nchw(up), x.repeat_interleave(2, 2).repeat_interleave(2, 3))
+    # adjoint
+    xg = xl.clone().requires_grad_(True)
+    dy = torch.randn(2, 12, 20, 40, generator=g).to(DEV, torch.bfloat16)
+    ops.upsample2x(xg).backward(dy)
+    ref = F.avg_pool2d(dy.float().permute(0, 3, 1, 2), 2) * 4
+    assert rel_err(nchw(xg.grad), ref.cpu()) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ convolutions
+def _conv_case(B, cin, cout, H, W, k, stride, pad_tl, residual, force_direct, seed=0, with_bias=True):
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = O.r16(torch.randn(B, cin, H, W, generator=g))
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = 0.1 * torch.randn(cout, generator=g) if with_bias else None
+    pt, pl = pad_tl
+    if stride == 2:   # Downsample: pad right/bottom by one (models/flux_ae.py:91-95)
+        xin = F.pad(x, (0, 1, 0, 1))
+        pad = 0
+    else:
+        xin, pad = x, pt
+    xr, wr = xin.clone().requires_grad_(True), O.r16(w).requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, b, stride=stride, padding=pad)
+    res = None
+    if residual:
+        res = O.r16(torch.randn(y_ref.shape, generator=g))
+        y_full = O.r16(O.r16(y_ref) + res)
+    else:
+        y_full = O.r16(y_ref)
+    dy = O.r16(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    dx_ref = xr.grad[..., :H, :W] if stride == 2 else xr.grad
+
+    pack = ops.WeightPack()
+    wf, wd = pack.get(w.to(DEV))
+    xc = nhwc(x)
+    y = ops.conv_forward_raw(xc, wf, None if b is None else b.to(DEV), None if res is None else nhwc(res), k, k, stride, pad_tl,
+                             force_direct=force_direct)
+    dyc = nhwc(dy)
+    dx = ops.conv_dgrad_raw(dyc, wf, wd, (H, W), k, k, stride, pad_tl, force_direct=force_direct)
+    dw = ops.conv_wgrad_raw(xc, dyc, k, k, stride, pad_tl, force_direct=force_direct)
+    db = ops.bias_grad_raw(dyc)
+    torch.cuda.synchronize()
+    # bf16 outputs (1 ulp = 2^-8); fp32 accumulation over K = cin*k*k terms
+    assert rel_err(nchw(y), y_full) < 4e-3, "forward"
+    assert rel_err(nchw(dx), dx_ref) < 4e-3, "dgrad"
+    assert rel_err(dw, wr.grad) < 1e-3, "wgrad"
+    assert rel_err(db, dy.sum((0, 2, 3))) < 1e-3, "bias grad"
+    # element-wise bound as well: |err| <= 2^-7 |ref| + 2^-8 * typical magnitude
+    yy, rr = nchw(y), y_full
+    assert ((yy - rr).abs() <= 2 ** -7 * rr.abs() + 2 ** -8 * rr.abs().mean()).all()
+
+
+@pytest.mark.parametrize("case", [
+    # B, cin, cout, H, W, k, stride, pad, residual
+    (2, 32, 32, 8, 8, 3, 1, (1, 1), False),      # decoder stem conv_in.0.conv
+    (1, 32, 64, 6, 10, 3, 1, (1, 1), True),
+    (2, 128, 3, 16, 16, 3, 1, (1, 1), False),    # conv_out head (Cout=3 kernel)
+    (2, 3, 64, 12, 12, 3, 1, (1, 1), False),     # encoder stem (Cin=3, scalar path)
+    (2, 64, 64, 8, 8, 3, 2, (0, 0), False),      # Downsample
+    (1, 64, 128, 9, 7, 1, 1, (0, 0), False),     # 1x1 on a ragged image
+    (1, 40, 24, 5, 5, 3, 1, (1, 1), False),
+])
+def test_conv_direct(case):
+    _conv_case(*case, force_direct=True)
+
+
+@pytest.mark.parametrize("case", [
+    (1, 64, 64, 8, 16, 3, 1, (1, 1), False),      # one tile, one k-chunk per tap, masked N
+    (2, 128, 128, 16, 16, 3, 1, (1, 1), True),    # BN=128, residual epilogue
+    (1, 64, 256, 16, 8, 1, 1, (0, 0), False),     # 1x1, BN=256
+    (2, 256, 512, 8, 32, 3, 1, (1, 1), False),    # 2 N tiles, 4 k-chunks
+    (1, 512, 512, 32, 32, 3, 1, (1, 1), True),    # decoder mid-block shape
+    (1, 128, 128, 4, 256, 3, 1, (1, 1), False),   # W=256 row tiles
+    (3, 32, 512, 32, 32, 3, 1, (1, 1), False),    # Cin=32: half-filled K chunk (TMA zero fill)
+    (1, 256, 128, 64, 64, 1, 1, (0, 0), False),   # nin_shortcut shape
+    (5, 128, 256, 16, 16, 3, 1, (1, 1), False),   # more tiles than one wave at small grid
+])
+def test_conv_tcgen05(case):
+    _conv_case(*case, force_direct=False)
+
+
+def test_conv_tc_many_tiles_matches_direct():
+    """Full-size layer (512->512 @64x64, B=2: 128 pixel tiles x 2 N tiles): tensor-core path vs CUDA-core path on device."""
+    ops, _ = _ops()
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(2, 64, 64, 512, generator=g, device=DEV).bfloat16()
+    w = (torch.randn(512, 512, 3, 3, generator=g, device=DEV) / 68).float()
+    b = torch.randn(512, generator=g, device=DEV)
+    wf, wd = ops.WeightPack().get(w)
+    y_tc = ops.conv_forward_raw(x, wf, b, None, 3, 3)
+    y_d = ops.conv_forward_raw(x, wf, b, None, 3, 3, force_direct=True)
+    assert rel_err(y_tc.float(), y_d.float()) < 3e-3
+    dy = torch.randn(2, 64, 64, 512, generator=g, device=DEV).bfloat16()
+    dw_tc = ops.conv_wgrad_raw(x, dy, 3, 3)
+    dw_d = ops.conv_wgrad_raw(x, dy, 3, 3, force_direct=True)
+    assert rel_err(dw_tc, dw_d) < 1e-3
