@@ -8,4 +8,4 @@ timeout 300 python -m pytest tests/test_kernels_gpu.py -q -k "tcgen05" > gpurun_
 echo "tc rc=$?" >> gpurun_out/k_tc.log
 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -k "conv_tc_many" > gpurun_out/k_tc_big.log 2>&1
 echo "tcbig rc=$?" >> gpurun_out/k_tc_big.log
-tail -5 gpurun_out/k_basic.log gpurun_out/k_tc.log gpurun_out/k_tc_big.log
+for f in k_basic k_tc k_tc_big; do tail -n 3 gpurun_out/$f.log; done

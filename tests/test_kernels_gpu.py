@@ -70,7 +70,8 @@ def test_dmd_nan_to_num_and_empty():
     loss.backward()
     assert torch.isfinite(zc.grad).all()
     assert rel_err(zc.grad, dz_ref) < 1e-5
-    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    # +-inf -> +-dtype max makes the squared error overflow to inf in the reference as well
+    assert loss.item() == loss_ref.item() or abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
     # empty batch
     e = torch.zeros(0, 4, 2, 2, device=DEV)
     loss, gn = L.dmd_loss(e, e, torch.zeros(0, device=DEV), e, e)
@@ -245,9 +246,11 @@ def _conv_case(B, cin, cout, H, W, k, stride, pad_tl, residual, force_direct, se
     assert rel_err(nchw(dx), dx_ref) < 4e-3, "dgrad"
     assert rel_err(dw, wr.grad) < 1e-3, "wgrad"
     assert rel_err(db, dy.sum((0, 2, 3))) < 1e-3, "bias grad"
-    # element-wise bound as well: |err| <= 2^-7 |ref| + 2^-8 * typical magnitude
+    # element-wise bound as well: one bf16 ulp (2^-8) of the larger of output / conv term (the residual add can
+    # cancel), plus fp32 accumulation-order noise scaled by the typical magnitude
     yy, rr = nchw(y), y_full
-    assert ((yy - rr).abs() <= 2 ** -7 * rr.abs() + 2 ** -8 * rr.abs().mean()).all()
+    mag = torch.maximum(rr.abs(), y_ref.detach().abs())
+    assert ((yy - rr).abs() <= 2 ** -7 * mag + 2 ** -8 * rr.abs().mean()).all()
 
 
 @pytest.mark.parametrize("case", [
