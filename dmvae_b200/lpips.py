@@ -1,0 +1,143 @@
+"""LPIPS with the reference's surface (utils/lpips.py:52-161) and a fused feature-distance reduction.
+
+State-dict keys are the reference's: ``scaling_layer.{shift,scale}``, ``net.slice{1..5}.{idx}.{weight,bias}``,
+``lin{0..4}.model.1.weight``.  The VGG16 convolutions stay library calls (cuDNN, channels-last bf16 under
+autocast; SURVEY.md row N3 is a later widening); everything after the taps -- channel-normalise, squared
+difference, 1x1 ``lin`` weighting, spatial mean (utils/lpips.py:86-91, ~50 ATen launches and six HBM passes in the
+reference) -- is one kernel per tap reading each feature map exactly once.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+from torch import nn
+
+from .losses import lpips_tap_distance
+
+_VGG_PLAN = [  # torchvision vgg16.features indices: (idx, kind, cin, cout)
+    (0, "c", 3, 64), (1, "r"), (2, "c", 64, 64), (3, "r"),
+    (4, "p"), (5, "c", 64, 128), (6, "r"), (7, "c", 128, 128), (8, "r"),
+    (9, "p"), (10, "c", 128, 256), (11, "r"), (12, "c", 256, 256), (13, "r"), (14, "c", 256, 256), (15, "r"),
+    (16, "p"), (17, "c", 256, 512), (18, "r"), (19, "c", 512, 512), (20, "r"), (21, "c", 512, 512), (22, "r"),
+    (23, "p"), (24, "c", 512, 512), (25, "r"), (26, "c", 512, 512), (27, "r"), (28, "c", 512, 512), (29, "r"),
+]
+_SLICE_END = (4, 9, 16, 23, 30)
+
+
+def _layer(spec):
+    if spec[1] == "c":
+        return nn.Conv2d(spec[2], spec[3], kernel_size=3, padding=1)
+    if spec[1] == "r":
+        return nn.ReLU(inplace=False)
+    return nn.MaxPool2d(kernel_size=2, stride=2)
+
+
+class vgg16(nn.Module):
+    """The five VGG16 slices ending at relu1_2, relu2_2, relu3_3, relu4_3, relu5_3 (utils/lpips.py:116-153)."""
+
+    def __init__(self, requires_grad=False, pretrained=True):
+        super().__init__()
+        self.N_slices = 5
+        start = 0
+        for k, end in enumerate(_SLICE_END, start=1):
+            seq = nn.Sequential()
+            for spec in _VGG_PLAN[start:end]:
+                seq.add_module(str(spec[0]), _layer(spec))
+            setattr(self, f"slice{k}", seq)
+            start = end
+        if pretrained:
+            self._try_load_imagenet()
+        if not requires_grad:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    def _try_load_imagenet(self):
+        try:
+            from torchvision.models import vgg16 as tv_vgg16
+            feats = tv_vgg16(weights="IMAGENET1K_V1").features.state_dict()   # needs a cached download
+            mapped = {}
+            for k, end in enumerate(_SLICE_END, start=1):
+                lo = 0 if k == 1 else _SLICE_END[k - 2]
+                for name, v in feats.items():
+                    if lo <= int(name.split(".")[0]) < end:
+                        mapped[f"slice{k}.{name}"] = v
+            self.load_state_dict(mapped, strict=True)
+        except Exception as e:  # offline: keep the default init, say so once
+            warnings.warn(f"LPIPS: ImageNet VGG16 weights unavailable ({type(e).__name__}); using random init")
+
+    def forward(self, X):
+        outs, h = [], X
+        for k in range(1, 6):
+            h = getattr(self, f"slice{k}")(h)
+            outs.append(h)
+        return outs
+
+
+class ScalingLayer(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("shift", torch.Tensor([-.030, -.088, -.188])[None, :, None, None])
+        self.register_buffer("scale", torch.Tensor([.458, .448, .450])[None, :, None, None])
+
+    def forward(self, inp):
+        return (inp - self.shift) / self.scale
+
+
+class NetLinLayer(nn.Module):
+    """Holds the 1x1 conv weight under the reference's key (``model.1.weight`` when dropout is configured)."""
+
+    def __init__(self, chn_in, chn_out=1, use_dropout=False):
+        super().__init__()
+        layers = [nn.Dropout()] if use_dropout else []
+        layers += [nn.Conv2d(chn_in, chn_out, 1, stride=1, padding=0, bias=False)]
+        self.model = nn.Sequential(*layers)
+
+    @property
+    def weight(self):
+        return self.model[-1].weight
+
+
+class LPIPS(nn.Module):
+    def __init__(self, ckpt_path=None, use_dropout=True, pretrained_vgg=True, faithful=None):
+        """faithful: reproduce the bf16 roundings autocast puts around the 1x1 lin conv and the bf16 tail
+        (None = do so exactly when autocast(bf16) is active, as the reference run would)."""
+        super().__init__()
+        self.scaling_layer = ScalingLayer()
+        self.chns = [64, 128, 256, 512, 512]
+        self.net = vgg16(pretrained=pretrained_vgg, requires_grad=False)
+        for k, c in enumerate(self.chns):
+            setattr(self, f"lin{k}", NetLinLayer(c, use_dropout=use_dropout))
+        self.faithful = faithful
+        if ckpt_path is not None:
+            self.load_from_pretrained(ckpt_path)
+        for p in self.parameters():
+            p.requires_grad = False
+
+    def load_from_pretrained(self, ckpt_path=None, name="vgg_lpips"):
+        if not os.path.exists(ckpt_path):
+            warnings.warn(f"LPIPS: {ckpt_path} not found; lin weights stay at their random init")
+            return
+        self.load_state_dict(torch.load(ckpt_path, map_location=torch.device("cpu"), weights_only=True), strict=False)
+
+    def forward(self, input, target):
+        """LPIPS(input, target) -> 0-d tensor; like the reference call LPIPS(images, recon) the gradient flows to
+        ``target`` (utils/lpips.py:81-94)."""
+        if self.training:
+            raise RuntimeError("LPIPS is an eval-only module here (reference: LPIPS(...).eval(), train_dmd.py:189)")
+        faithful = self.faithful
+        if faithful is None:
+            faithful = torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+        cl = torch.channels_last
+        with torch.no_grad():
+            f0 = self.net(self.scaling_layer(input).contiguous(memory_format=cl))
+        f1 = self.net(self.scaling_layer(target).contiguous(memory_format=cl))
+        val = None
+        for k in range(5):
+            w = getattr(self, f"lin{k}").weight
+            d = lpips_tap_distance(f0[k], f1[k], w, faithful)            # (B,) spatial means
+            if faithful:
+                d = d.to(torch.bfloat16)
+            val = d if val is None else val + d
+        return val.mean()
