@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- VAE(+DMD) training images/sec at 256x256, bf16, on N B200s.
+
+A "step" is one pass of the hot path over one synthetic batch: the VAE-pretrain step of train_tokenizer.py:403-437
+(BASELINE.json configs[1]): frozen DINOv2 ViT-L/16 encoder -> bottleneck MLP -> flux Decoder forward, L1 + LPIPS(VGG16)
+reconstruction loss, backward through the decoder, gradient allreduce, clip, AdamW, EMA -- per-GPU batch 16
+(scripts/train_tokenizer.sh:30).
+
+    python bench.py [--gpus N --steps K --warmup W]            # our arm
+    python bench.py --impl reference [...]                     # CPU arm: the oracle port on the host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      # one rank per GPU
+
+One JSON line on stdout (rank 0).  `value` = device-resident inputs, no host syncs in the timed region;
+`e2e` = the same K steps through the public API with pinned HOST image batches copied in and the loss read back
+every step.  `roofline` is the tcgen05 conv tile (forward + data-gradient launches) timed with CUDA events around
+every launch of one extra profiled step; `cpu_baseline` is the oracle step timed on a bounded sample (1 image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+
+import torch  # noqa: E402
+
+METRIC = "VAE+DMD training images/sec (256^2, bf16)"
+UNIT = "images/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ algorithmic work per call
+def _work(name, a):
+    """FLOPs for the conv entry points (2*M*N*K, bias/GN excluded -- SURVEY.md section 8(d)); 0 otherwise."""
+    if name == "dmvae_conv_tc_fwd":        # x, w, bias, res, y, B, H, W, Cin, Cout, KH, KW
+        B, H, W, cin, cout, kh, kw = a[5:12]
+        return 2.0 * B * H * W * cin * cout * kh * kw
+    if name == "dmvae_conv_tc_wgrad":      # x, dy, dw, B, H, W, Cin, Cout, KH, KW
+        B, H, W, cin, cout, kh, kw = a[3:10]
+        return 2.0 * B * H * W * cin * cout * kh * kw
+    if name == "dmvae_conv_direct_fwd":    # x, w, bias, res, y, B,H,W,Cin,OH,OW,Cout,KH,KW,...
+        B, H, W, cin, OH, OW, cout, kh, kw = a[5:14]
+        return 2.0 * B * OH * OW * cin * cout * kh * kw
+    if name == "dmvae_conv_direct_wgrad":
+        B, H, W, cin, OH, OW, cout, kh, kw = a[3:12]
+        return 2.0 * B * OH * OW * cin * cout * kh * kw
+    return 0.0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def build_trainer(device, model_size="large", z_channels=32):
+    from dmvae_b200.lpips import LPIPS
+    from dmvae_b200.train import LossConfig, TokenizerTrainer, VAELossFunction
+    from dmvae_b200.vae import VAE
+    torch.manual_seed(42)
+    vae = VAE(z_channels=z_channels, model_size=model_size).to(device)
+    vae.encoder.eval()
+    for p in vae.encoder.parameters():           # train_tokenizer.py:295-297
+        p.requires_grad = False
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        lp = LPIPS(ckpt_path=os.path.join(ROOT, "ckpt_vae", "vgg.pth") if os.path.exists(os.path.join(ROOT, "ckpt_vae", "vgg.pth")) else None,
+                   pretrained_vgg=False).eval().to(device)
+    cfg = LossConfig(l1=1.0, l2=0.0, lpips=1.0, dmd_weight=0.0)
+    return TokenizerTrainer(vae, VAELossFunction(cfg, lpips_loss=lp), lr=1e-4)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from dmvae_b200 import _lib
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    B = args.batch
+    tr = build_trainer(dev)
+    g = torch.Generator().manual_seed(42 * world + rank)
+    n_pool = 4
+    host = [(torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).pin_memory() for _ in range(n_pool)]
+    resident = [h.to(dev) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(args.warmup):
+        tr.step(resident[i % n_pool])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.Stats.reset()
+    ms = timed(lambda i: tr.step(resident[i % n_pool]), args.steps)
+    launches = _lib.Stats.launches
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end: pinned host batch in, loss out, every step
+    last = {}
+
+    def e2e_step(i):
+        x = host[i % n_pool].to(dev, non_blocking=True)
+        last["loss"] = tr.step(x)["loss"].item()
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # one profiled step: CUDA events around every library launch
+    _lib.Stats.reset()
+    _lib.Stats.work_fn = _work
+    _lib.Stats.timing = True
+    tr.step(resident[0])
+    torch.cuda.synchronize()
+    _lib.Stats.timing = False
+    per = {}
+    for name, a, b, work in _lib.Stats.events:
+        d = per.setdefault(name, [0, 0.0, 0.0])
+        d[0] += 1; d[1] += a.elapsed_time(b); d[2] += work
+    step_ms_prof = sum(v[1] for v in per.values())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    tc = per.get("dmvae_conv_tc_fwd", [0, 0.0, 0.0])
+    achieved = tc[2] / (tc[1] * 1e-3) / 1e12 if tc[1] > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, fwd + dgrad launches)",
+            "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+            "frac": round(achieved / peaks["tf_sustained"], 4), "peak_source": f"{peaks['src']} (sustained: kernel timed inside a long step)",
+            "launches_per_step": tc[0], "avg_launch_ms": round(tc[1] / max(tc[0], 1), 4),
+            "flops_per_launch_avg": tc[2] / max(tc[0], 1), "traffic": None,
+            "share_of_step": round(tc[1] / max(step_ms_prof, 1e-9), 4)}
+    wg = per.get("dmvae_conv_tc_wgrad", [0, 0.0, 0.0])
+    kernels = {k.replace("dmvae_", ""): {"n": v[0], "ms": round(v[1], 3), **({"tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1)} if v[2] and v[1] else {})}
+               for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])}
+    imgs = world * B * args.steps
+    out = {
+        "metric": METRIC, "value": round(imgs / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "train_tokenizer.py VAE pretrain step (BASELINE configs[1]): frozen ViT-L/16 encoder, flux Decoder "
+                               "fwd+bwd, L1+LPIPS(VGG16), allreduce, clip, AdamW, EMA", "per_gpu_batch": B, "global_batch": B * world,
+                   "image": "3x256x256", "z_channels": 32, "parallelism": f"dp{world}", "weights": "random init (seed 42)",
+                   "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; 4 rotating input batches"},
+        "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": B * 3 * 256 * 256 * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last.get("loss")},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "wgrad": {"achieved_tflops": round(wg[2] / (wg[1] * 1e-3) / 1e12, 1) if wg[1] else None, "launches_per_step": wg[0]},
+        "kernels_ms_per_step": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_step_baseline(sample_images=1, reps=1)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+class OracleStep:
+    """The same training step on the host cores: oracle/dmvae_oracle.py (decoder + losses, fp32, autograd) with the
+    stock-PyTorch encoder module run on CPU, AdamW on the decoder/bottleneck tensors."""
+
+    def __init__(self):
+        from oracle import dmvae_oracle as O
+        from dmvae_b200.vae import DINOEncoder, MLP
+        self.O = O
+        torch.manual_seed(42)
+        self.enc = DINOEncoder("large").eval()
+        self.mlp = MLP(1024, 32)
+        self.sd = {k: v.requires_grad_(True) for k, v in O.make_decoder_state(z_channels=32, seed=42).items()}
+        self.lp = O.make_lpips_state(seed=42)
+        self.params = list(self.sd.values()) + list(self.mlp.parameters())
+        self.opt = torch.optim.AdamW(self.params, lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
+
+    def step(self, images):
+        O = self.O
+        with torch.no_grad():
+            tok = self.enc(images)
+        z = self.mlp(tok)
+        recon = O.decoder_forward(self.sd, z)
+        loss = (recon - images).abs().mean() + O.lpips_forward(self.lp, images, recon)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.params, 1.0)
+        self.opt.step()
+        return loss.item()
+
+
+def cpu_step_baseline(sample_images=1, reps=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = OracleStep()
+    x = torch.rand(sample_images, 3, 256, 256, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    st.step(x)                                   # warm-up (thread pool, oneDNN primitive caches)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        st.step(x)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": round(sample_images / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} oracle step(s) of {sample_images} image(s) after 1 warm-up, fp32, torch.set_num_threads({cores})"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = OracleStep()
+    b = args.ref_batch
+    g = torch.Generator().manual_seed(42)
+    xs = [torch.rand(b, 3, 256, 256, generator=g) * 2 - 1 for _ in range(2)]
+    for i in range(args.warmup):
+        st.step(xs[i % 2])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        loss = st.step(xs[i % 2])
+    dt = time.perf_counter() - t0
+    v = round(b * args.steps / dt, 4)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "train_tokenizer.py VAE pretrain step (BASELINE configs[1]) on the host cores: oracle port of the "
+                               "reference's PyTorch modules (the Python reference itself does not travel to the GPU box)",
+                   "per_step_batch": b, "image": "3x256x256", "z_channels": 32},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of {b} image(s) after {args.warmup} warm-up"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "last_loss": loss}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (scripts/train_tokenizer.sh: local_bs 16)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -95,6 +95,24 @@ def dtype_code(t: torch.Tensor) -> int:
     raise DmvaeError(f"unsupported dtype {t.dtype} (float32 / bfloat16 only)")
 
 
+# kernels launched per entry point (everything else launches exactly one)
+_LAUNCHES = {"dmvae_gn_bwd": 2}
+
+
+class Stats:
+    """Launch accounting and optional per-entry-point device timing (CUDA events on the launching stream).
+    bench.py turns ``timing`` on for a profiled step; the timed region runs with it off."""
+    launches = 0
+    timing = False
+    events = []          # (name, start_event, end_event, work) ; work = algorithmic flops or bytes, see bench.py
+    work_fn = None       # callable(name, args) -> float
+
+    @classmethod
+    def reset(cls):
+        cls.launches = 0
+        cls.events = []
+
+
 def call(name: str, *args) -> None:
     """Invoke a compute entry point on the current CUDA stream; raises DmvaeError on failure."""
     global _device_ok
@@ -105,7 +123,15 @@ def call(name: str, *args) -> None:
         if lib.dmvae_check_device() != 0:
             raise DmvaeError(lib.dmvae_last_error().decode())
         _device_ok = True
-    rc = getattr(lib, name)(*args, _stream())
+    Stats.launches += _LAUNCHES.get(name, 1)
+    if Stats.timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, _stream())
+        e1.record()
+        Stats.events.append((name, e0, e1, Stats.work_fn(name, args) if Stats.work_fn else 0.0))
+    else:
+        rc = getattr(lib, name)(*args, _stream())
     if rc != 0:
         raise DmvaeError(f"{name} failed ({rc}): {lib.dmvae_last_error().decode()}")
 

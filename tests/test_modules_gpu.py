@@ -1,0 +1,189 @@
+"""Module-level parity on the GPU: the drop-in nn.Modules (dmvae_b200.autoencoder / vae / lpips / train) against the
+CPU oracle run in its autocast-emulating mode (bf16=True) on identical weights and inputs.
+
+Tolerance: activations are bf16 (ulp 2^-8 = 3.9e-3); through a stack of L conv+GN layers independent roundings add
+in quadrature, so norm-wise relative error is bounded by ~2^-8*sqrt(L): 2e-2 for the decoders here."""
+import copy
+import os
+
+import pytest
+import torch
+
+from oracle import dmvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _decoder(sd, **kw):
+    from dmvae_b200.autoencoder import Decoder
+    d = Decoder(**kw)
+    if "conv_in.0.conv.weight" in sd:
+        d.post_init(sd["conv_in.0.conv.weight"].shape[0])
+    d.load_state_dict(sd, strict=True)          # reference-keyed state_dict must load as is
+    return d.to(DEV)
+
+
+def test_decoder_tiny_golden_weights_fwd_bwd():
+    c = torch.load(os.path.join(G, "flux_ae.pt"), weights_only=True)["decoder_tiny"]
+    dec = _decoder(c["sd"], ch=32, out_ch=3, ch_mult=(1, 2), num_res_blocks=1, in_channels=3, resolution=16, z_channels=4)
+    # oracle, autocast-emulating
+    sd = {k: v.clone().requires_grad_(True) for k, v in c["sd"].items()}
+    z = c["z"].clone().requires_grad_(True)
+    y_ref = O.decoder_forward(sd, z, bf16=True)
+    y_ref.backward(c["dy"])
+    zc = c["z"].to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = dec(zc)
+    assert y.dtype == torch.bfloat16 and y.shape == y_ref.shape
+    y.backward(c["dy"].to(DEV, torch.bfloat16))
+    assert rel(y.float(), y_ref) < 2e-2
+    assert rel(zc.grad, z.grad) < 3e-2
+    for name in ("conv_out.weight", "mid.block_1.conv1.weight", "conv_in.0.conv.weight", "up.1.block.0.norm1.weight",
+                 "mid.attn_1.q.weight", "up.0.block.0.nin_shortcut.weight", "conv_out.bias"):
+        g = dict(dec.named_parameters())[name].grad
+        assert rel(g, sd[name].grad) < 3e-2, name
+    # and against the real reference's fp32 output: bf16 pipeline vs fp32 pipeline
+    assert rel(y.float(), c["y"]) < 3e-2
+
+
+def test_decoder_tensor_core_path_tokens():
+    """ch=64 decoder on (B,256,32) tokens: 128/64-channel layers at 32x32 / 64x64 run on the tcgen05 tile."""
+    sd = O.make_decoder_state(ch=64, ch_mult=(1, 2), num_res_blocks=1, z_channels=32, seed=3, std=0.05, randomize_affine=True)
+    dec = _decoder(sd, ch=64, out_ch=3, ch_mult=(1, 2), num_res_blocks=1, in_channels=3, resolution=64, z_channels=32)
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(2, 256, 32, generator=g)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    zr = z.clone().requires_grad_(True)
+    y_ref = O.decoder_forward(sdr, zr, bf16=True)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    zc = z.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = dec(zc)
+    y.backward(dy.to(DEV, torch.bfloat16))
+    assert rel(y.float(), y_ref) < 2e-2
+    assert rel(zc.grad, zr.grad) < 3e-2
+    params = dict(dec.named_parameters())
+    for name in ("conv_out.weight", "mid.block_2.conv2.weight", "up.1.block.1.conv1.weight", "up.1.upsample.conv.weight",
+                 "up.0.block.0.conv1.weight", "conv_in.1.weight", "mid.attn_1.proj_out.weight", "norm_out.weight",
+                 "up.0.block.1.conv2.bias"):
+        assert rel(params[name].grad, sdr[name].grad) < 3e-2, name
+
+
+def test_decoder_full_size_forward():
+    """The production decoder (49.6 M params, 620 GFLOP) on one image, every layer on its production kernel."""
+    sd = O.make_decoder_state(z_channels=32, seed=1, std=0.02, randomize_affine=True)
+    dec = _decoder(sd, ch=128, out_ch=3, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, resolution=256, z_channels=16)
+    z = torch.randn(1, 256, 32, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        y_ref = O.decoder_forward(sd, z, bf16=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16), torch.inference_mode():
+        y = dec(z.to(DEV))
+    assert y.shape == (1, 3, 256, 256)
+    assert rel(y.float(), y_ref) < 3e-2
+
+
+def test_encoder_small_and_reparam():
+    from dmvae_b200.autoencoder import Encoder
+    from dmvae_b200 import losses
+    sd = O.make_encoder_state(ch=32, ch_mult=(1, 2, 2), num_res_blocks=1, z_channels=4, seed=4, std=0.05, randomize_affine=True)
+    enc = Encoder(resolution=64, in_channels=3, ch=32, ch_mult=(1, 2, 2), num_res_blocks=1, z_channels=4)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    h_ref = O.encoder_forward(sdr, x, bf16=True)
+    eps = torch.randn(2, 4, 16, 16, generator=g)
+    z_ref, kl_ref = O.reparam_kl(*h_ref.chunk(2, 1), eps)
+    (z_ref.square().mean() + 1e-3 * kl_ref).backward()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        h = enc(x.to(DEV))
+        z, kl = losses.reparam_kl(h, eps.to(DEV), channel_dim=1)
+    (z.float().square().mean() + 1e-3 * kl).backward()
+    assert rel(h.float(), h_ref) < 2e-2
+    assert abs(kl.item() - kl_ref.item()) < 2e-2 * abs(kl_ref.item())
+    p = dict(enc.named_parameters())
+    for name in ("conv_in.weight", "down.0.downsample.conv.weight", "conv_out.weight", "mid.block_1.conv1.weight"):
+        assert rel(p[name].grad, sdr[name].grad) < 4e-2, name
+
+
+def test_retain_graph_partial_grads_and_inference_mode():
+    """The adaptive-weight code (train_dmd.py:248-251) calls autograd.grad(..., retain_graph=True) twice on
+    conv_out.weight before the real backward; encode/decode run under inference_mode (models/vae.py:100-108)."""
+    sd = O.make_decoder_state(ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=8, seed=5, std=0.05)
+    dec = _decoder(sd, ch=32, out_ch=3, ch_mult=(1, 2), num_res_blocks=1, in_channels=3, resolution=64, z_channels=8)
+    z = torch.randn(1, 256, 8, device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = dec(z).float()
+        l_a, l_b = y.abs().mean(), y.square().mean()
+    last = dec.get_last_layer()
+    g1 = torch.autograd.grad(l_a, last, retain_graph=True)[0]
+    g2 = torch.autograd.grad(l_b, last, retain_graph=True)[0]
+    (l_a + l_b).backward()
+    assert rel(last.grad, g1 + g2) < 1e-5
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y2 = dec(z)
+    assert torch.equal(y2.float(), y.detach())          # same kernels, deterministic forward
+    ema = copy.deepcopy(dec)                            # EMA copy (train_tokenizer.py:397)
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        assert torch.equal(ema(z), y2)
+    with torch.no_grad():                               # weight update must invalidate the packed bf16 operands
+        dec.conv_out.weight.mul_(2.0); dec.conv_out.bias.mul_(2.0)
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y3 = dec(z)
+    assert rel(y3.float(), 2 * y2.float()) < 1e-2
+
+
+def test_lpips_module_vs_oracle_fp32():
+    from dmvae_b200.lpips import LPIPS
+    torch.backends.cudnn.allow_tf32 = False
+    sd = O.make_lpips_state(seed=2)
+    lp = LPIPS(ckpt_path=None, pretrained_vgg=False)
+    missing = lp.load_state_dict(sd, strict=True)
+    lp = lp.eval().to(DEV)
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    b = (a + 0.2 * torch.randn(a.shape, generator=g)).clamp(-1, 1)
+    br = b.clone().requires_grad_(True)
+    ref = O.lpips_forward(sd, a, br)
+    ref.backward()
+    bc = b.to(DEV).requires_grad_(True)
+    val = lp(a.to(DEV), bc)
+    val.backward()
+    assert abs(val.item() - ref.item()) < 1e-3 * abs(ref.item())
+    assert rel(bc.grad, br.grad) < 1e-2
+    # autocast run: within the reference's own bf16 noise (outputs are bf16: 2^-8)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        v16 = lp(a.to(DEV), b.to(DEV))
+    ref16 = O.lpips_forward(sd, a, b, bf16=True)
+    assert abs(v16.float().item() - ref16.item()) < 3e-2 * abs(ref16.item())
+
+
+def test_tokenizer_trainer_steps_and_loss_goes_down():
+    from dmvae_b200.vae import VAE
+    from dmvae_b200.lpips import LPIPS
+    from dmvae_b200.train import LossConfig, TokenizerTrainer, VAELossFunction
+    torch.manual_seed(0)
+    vae = VAE(z_channels=32, model_size="base").to(DEV)
+    vae.encoder.eval()
+    for p in vae.encoder.parameters():
+        p.requires_grad = False
+    lp = LPIPS(ckpt_path=None, pretrained_vgg=False).eval().to(DEV)
+    tr = TokenizerTrainer(vae, VAELossFunction(LossConfig(), lpips_loss=lp), lr=2e-4)
+    imgs = torch.rand(2, 3, 256, 256, device=DEV) * 2 - 1
+    first = last = None
+    for i in range(6):
+        log = tr.step(imgs)
+        v = log["loss"].item()
+        assert v == v and abs(v) < 1e4
+        first = v if first is None else first
+        last = v
+    assert last < first
