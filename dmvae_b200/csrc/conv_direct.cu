@@ -138,6 +138,124 @@ __global__ void __launch_bounds__(128) conv_small_cout_fwd_kernel(const bf16* __
     for (int c = 0; c < CO; ++c) y[m * CO + c] = __float2bfloat16_rn(acc[c] + (bias ? bias[c] : 0.f));
 }
 
+
+// ---- thin-input conv: Cin <= 4 (encoder stem 3->128, and the data-gradient of the 128->3 head) ---------------------
+// Each thread produces 8 output channels for two horizontally adjacent pixels; the 27 x 8 weights it needs are read
+// from shared memory once per pixel pair.  3x3, stride 1, pad 1.
+template <int CI>
+__global__ void __launch_bounds__(256) conv_thin_in_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                               const float* __restrict__ bias, bf16* __restrict__ y, ConvGeom g) {
+    extern __shared__ float sw[];                 // [tap*CI + ci][Cout]  (co fastest -> conflict-free LDS.128)
+    for (int i = threadIdx.x; i < 9 * CI * g.Cout; i += blockDim.x) {
+        const int co = i % g.Cout, tc = i / g.Cout;           // tc = tap*CI + ci
+        sw[i] = __bfloat162float(w[((int64_t)(tc / CI) * g.Cout + co) * CI + (tc % CI)]);
+    }
+    __syncthreads();
+    const int vc = g.Cout / 8;
+    const int col = threadIdx.x % vc;
+    const int64_t pairs = (int64_t)g.B * g.H * (g.W / 2);
+    const int ppb = blockDim.x / vc;
+    float bs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bs[k] = bias ? bias[col * 8 + k] : 0.f;
+    for (int64_t pr = (int64_t)blockIdx.x * ppb + threadIdx.x / vc; pr < pairs; pr += (int64_t)gridDim.x * ppb) {
+        const int w0 = (int)(pr % (g.W / 2)) * 2;
+        const int h = (int)((pr / (g.W / 2)) % g.H);
+        const int64_t b = pr / ((int64_t)(g.W / 2) * g.H);
+        float a0[8], a1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a0[k] = bs[k]; a1[k] = bs[k]; }
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int ih = h + kh - 1;
+            if (ih < 0 || ih >= g.H) continue;
+            const bf16* xrow = x + ((b * g.H + ih) * g.W) * CI;
+            // the two pixels share columns w0-1 .. w0+2
+            float xv[4][CI];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int iw = w0 - 1 + j;
+                const bool ok = iw >= 0 && iw < g.W;
+#pragma unroll
+                for (int c = 0; c < CI; ++c) xv[j][c] = ok ? __bfloat162float(xrow[(int64_t)iw * CI + c]) : 0.f;
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                for (int c = 0; c < CI; ++c) {
+                    const float* wp = sw + ((kh * 3 + kw) * CI + c) * g.Cout + col * 8;
+                    const float4 wa = *reinterpret_cast<const float4*>(wp), wb = *reinterpret_cast<const float4*>(wp + 4);
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    const float x0 = xv[kw][c], x1 = xv[kw + 1][c];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { a0[k] += x0 * wv[k]; a1[k] += x1 * wv[k]; }
+                }
+        }
+        bf16* yp = y + (((b * g.H + h) * g.W) + w0) * g.Cout + col * 8;
+        st_stream16(yp, pack_bf16x8(a0));
+        st_stream16(yp + g.Cout, pack_bf16x8(a1));
+    }
+}
+
+// ---- thin weight gradient: one operand has <= 4 channels (the 128->3 head: dy thin; the 3->128 stem: x thin) ------
+// Threads own one channel of the wide operand and keep 9 x T accumulators; the thin operand's rows (with halo) sit
+// in shared memory and are read by warp-wide broadcast.  3x3, stride 1, pad 1.
+//   THIN_IS_DY = true : dw[t][wide][tap] += dy[q][t] * x[p][wide],  q = p - (tap offset)   (loop over x pixels p)
+//   THIN_IS_DY = false: dw[wide][t][tap] += x[p][t] * dy[q][wide],  p = q + (tap offset)   (loop over dy pixels q)
+template <int T, bool THIN_IS_DY>
+__global__ void __launch_bounds__(256) conv_thin_wgrad_kernel(const bf16* __restrict__ wide, const bf16* __restrict__ thin,
+                                                              float* __restrict__ dw, int B, int H, int W, int CW, int rows_per_block) {
+    extern __shared__ float sm[];                 // thin rows [rows_per_block + 2][W][T], then the fan-in buffer
+    const int blocks_per_img = (H + rows_per_block - 1) / rows_per_block;
+    const int b = blockIdx.x / blocks_per_img;
+    const int r0 = (blockIdx.x % blocks_per_img) * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, H);
+    const int nrows = r1 - r0 + 2;
+    for (int i = threadIdx.x; i < nrows * W * T; i += blockDim.x) {
+        const int rr = r0 - 1 + i / (W * T);
+        sm[i] = (rr >= 0 && rr < H) ? __bfloat162float(thin[((int64_t)b * H + rr) * W * T + i % (W * T)]) : 0.f;
+    }
+    __syncthreads();
+    const int halves = blockDim.x / CW > 0 ? blockDim.x / CW : 1;      // pixel-range split when CW < blockDim
+    const int c = threadIdx.x % CW, part = threadIdx.x / CW;
+    const int sgn = THIN_IS_DY ? -1 : 1;
+    if (part < halves) {
+        for (int cw = c; cw < CW; cw += blockDim.x) {
+            float acc[9][T];
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+                for (int t = 0; t < T; ++t) acc[tp][t] = 0.f;
+            for (int r = r0; r < r1; ++r) {
+                const bf16* wrow = wide + (((int64_t)b * H + r) * W) * CW + cw;
+                for (int wq = part; wq < W; wq += halves) {
+                    const float v = __bfloat162float(wrow[(int64_t)wq * CW]);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const int tr = r + sgn * (kh - 1);                 // thin row
+                        if (tr < 0 || tr >= H) continue;
+                        const float* trow = sm + (tr - r0 + 1) * W * T;
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const int tw = wq + sgn * (kw - 1);
+                            if (tw < 0 || tw >= W) continue;
+#pragma unroll
+                            for (int t = 0; t < T; ++t) acc[kh * 3 + kw][t] += trow[tw * T + t] * v;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const int64_t idx = THIN_IS_DY ? (((int64_t)t * CW + cw) * 9 + tp) : (((int64_t)cw * T + t) * 9 + tp);
+                    atomicAdd(&dw[idx], acc[tp][t]);
+                }
+        }
+    }
+}
+
 static int check_geom(const ConvGeom& g, const char* who) {
     if (g.B < 0 || g.H <= 0 || g.W <= 0 || g.Cin <= 0 || g.Cout <= 0 || g.KH <= 0 || g.KW <= 0 || g.stride <= 0)
         return dmvae_set_error(DMVAE_EINVAL, "%s: bad geometry", who);
@@ -167,6 +285,17 @@ DMVAE_API int dmvae_conv_direct_fwd(const void* x, const void* w_packed, const f
         switch (Cout) { case 1: SMALL(1) break; case 2: SMALL(2) break; case 3: SMALL(3) break; default: SMALL(4) break; }
 #undef SMALL
         DMVAE_CHECK_LAUNCH("conv_small_cout_fwd_kernel");
+        return DMVAE_OK;
+    }
+    if (Cin == 3 && KH == 3 && KW == 3 && stride == 1 && pad_top == 1 && pad_left == 1 && OH == H && OW == W && !residual &&
+        Cout % 8 == 0 && Cout <= 1024 && 256 % (Cout / 8) == 0 && W % 2 == 0 && (((uintptr_t)y & 15) == 0)) {
+        const size_t smem = (size_t)27 * Cout * sizeof(float);
+        cudaFuncSetAttribute(conv_thin_in_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        const int ppb = 256 / (Cout / 8);
+        int64_t blocks = ceil_div64((int64_t)B * H * (W / 2), ppb);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        conv_thin_in_fwd_kernel<3><<<(unsigned)blocks, 256, smem, st>>>((const bf16*)x, (const bf16*)w_packed, bias, (bf16*)y, g);
+        DMVAE_CHECK_LAUNCH("conv_thin_in_fwd_kernel");
         return DMVAE_OK;
     }
     dim3 grid((unsigned)ceil_div64(M, CD_BM), (unsigned)((Cout + CD_BN - 1) / CD_BN));
@@ -344,6 +473,21 @@ DMVAE_API int dmvae_conv_direct_wgrad(const void* x, const void* dy, float* dw, 
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t M = (int64_t)B * OH * OW;
     const int taps = KH * KW;
+    const bool same3 = KH == 3 && KW == 3 && stride == 1 && pad_top == 1 && pad_left == 1 && OH == H && OW == W;
+    if (same3 && (Cout == 3 || Cin == 3) && (Cout == 3 ? Cin : Cout) <= 256 && W <= 1024) {
+        const int rpb = 8;
+        const size_t smem = (size_t)(rpb + 2) * W * 3 * sizeof(float);
+        const int blocks = B * ((H + rpb - 1) / rpb);
+        if (Cout == 3) {
+            cudaFuncSetAttribute(conv_thin_wgrad_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            conv_thin_wgrad_kernel<3, true><<<blocks, 256, smem, st>>>((const bf16*)x, (const bf16*)dy, dw, B, H, W, Cin, rpb);
+        } else {
+            cudaFuncSetAttribute(conv_thin_wgrad_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            conv_thin_wgrad_kernel<3, false><<<blocks, 256, smem, st>>>((const bf16*)dy, (const bf16*)x, dw, B, H, W, Cout, rpb);
+        }
+        DMVAE_CHECK_LAUNCH("conv_thin_wgrad_kernel");
+        return DMVAE_OK;
+    }
     if (Cout <= 4 && taps == 9 && Cout == 3) {
         int64_t blocks = 148 * 8;
         int64_t mpb = ceil_div64(M, blocks);
@@ -387,15 +531,59 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__
     }
 }
 
+// vectorised variant: threads own a fixed 8-channel column, 4 x 16 B loads in flight, shared-memory fan-in
+__global__ void __launch_bounds__(256) bias_grad_vec_kernel(const bf16* __restrict__ dy, float* __restrict__ db, int64_t M,
+                                                            int C, int vc, int rows, int64_t m_per_block) {
+    extern __shared__ float s_acc[];   // [C]
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_acc[c] = 0.f;
+    __syncthreads();
+    const int col = threadIdx.x % vc, row = threadIdx.x / vc;
+    const int64_t ms = (int64_t)blockIdx.x * m_per_block;
+    const int64_t me = (ms + m_per_block < M) ? ms + m_per_block : M;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bf16* base = dy + col * 8;
+    constexpr int U = 4;
+    for (int64_t m = ms + row; m < me; m += (int64_t)rows * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t mm = m + (int64_t)u * rows;
+            v[u] = mm < me ? ld_stream16(base + mm * C) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float f[8];
+            unpack_bf16x8(v[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += f[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[col * 8 + k], a[k]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&db[c], s_acc[c]);
+}
+
 DMVAE_API int dmvae_bias_grad(const void* dy, float* dbias, int64_t M, int C, void* stream) {
     DMVAE_CHECK_ARG(dy && dbias, "bias_grad: null pointer");
     DMVAE_CHECK_ARG(M >= 0 && C > 0, "bias_grad: bad shape");
     if (M == 0) return DMVAE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && ((uintptr_t)dy & 15) == 0) {
+        const int vc = C / 8, rows = 256 / vc;
+        int64_t blocks = 148 * 8;
+        int64_t mpb = ceil_div64(M, blocks);
+        if (mpb < (int64_t)rows * 8) mpb = (int64_t)rows * 8;
+        blocks = ceil_div64(M, mpb);
+        bias_grad_vec_kernel<<<(unsigned)blocks, 256, C * sizeof(float), st>>>((const bf16*)dy, dbias, M, C, vc, rows, mpb);
+        DMVAE_CHECK_LAUNCH("bias_grad_vec_kernel");
+        return DMVAE_OK;
+    }
     int64_t blocks = 148 * 4;
     int64_t mpb = ceil_div64(M, blocks);
     if (mpb < 64) mpb = 64;
     blocks = ceil_div64(M, mpb);
-    bias_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, dbias, M, C, mpb);
+    bias_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>((const bf16*)dy, dbias, M, C, mpb);
     DMVAE_CHECK_LAUNCH("bias_grad_kernel");
     return DMVAE_OK;
 }

@@ -124,12 +124,12 @@ struct TcGeom {
 };
 
 template <int BN> struct Cfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers (256 or 512 columns)
+    static constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers (64, 256 or 512 columns)
 };
 
 template <int BN>
@@ -236,7 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (n >= g.Cout) continue;                            // warp-uniform
                 bf16* op = out + pix * g.Cout + n;
                 const bf16* rp = res ? res + pix * g.Cout + n : nullptr;
-                if (n + 32 <= g.Cout) {
+                if (n + 32 <= g.Cout && (g.Cout & 7) == 0) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float f[8];
@@ -533,7 +533,8 @@ int launch_conv_tc(const void* x, const void* w, const float* bias, const void* 
 // 1 if (shape) can run on the tcgen05 tile, else 0 (caller uses conv_direct)
 DMVAE_API int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW) {
     int bw, bh;
-    if (B <= 0 || Cin % 8 != 0 || Cout % 8 != 0 || Cin < 32 || Cout < 32) return 0;
+    // Cout may be tiny (the 128->3 head runs as an N=32 tile with TMA zero-filled weight rows and masked stores)
+    if (B <= 0 || Cin % 8 != 0 || Cin < 32 || Cout < 1 || (Cout > 32 && Cout % 8 != 0)) return 0;
     if (!((KH == 3 && KW == 3) || (KH == 1 && KW == 1))) return 0;
     return pick_pixel_tile(H, W, &bw, &bh);
 }
@@ -555,6 +556,10 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     g.m_tiles = B * g.tiles_w * g.tiles_h;
     g.k_chunks = (Cin + BK - 1) / BK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (Cout <= 32) {
+        g.n_tiles = 1;
+        return launch_conv_tc<32>(x, w_packed, bias, residual, y, g, st);
+    }
     if (Cout % 256 == 0 || Cout > 256) {
         g.n_tiles = (Cout + 255) / 256;
         return launch_conv_tc<256>(x, w_packed, bias, residual, y, g, st);

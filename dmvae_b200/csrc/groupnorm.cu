@@ -10,6 +10,7 @@
 
 #define GN_GROUPS 32
 #define GN_THREADS 256
+#define GN_UNROLL 4
 
 struct GnGeom {
     int vc;        // 16-byte vectors per pixel  (C / 8)
@@ -26,8 +27,8 @@ static int gn_geom(int C, GnGeom* g, const char* who) {
 
 static void gn_grid(int64_t B, int64_t HW, int rows, dim3* grid, int64_t* ppb) {
     // aim for >= 4 waves of 148 SMs x 2 CTAs, but at least 4 passes of work per CTA
-    int64_t chunks = (148 * 8 + B - 1) / B;
-    int64_t max_chunks = ceil_div64(HW, (int64_t)rows * 4);
+    int64_t chunks = (148 * 16 + B - 1) / B;
+    int64_t max_chunks = ceil_div64(HW, (int64_t)rows * 8);
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     *ppb = ceil_div64(HW, chunks);
@@ -50,11 +51,20 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __rest
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
     const bf16* base = x + (int64_t)b * HW * C + col * 8;
-    for (int64_t p = p0 + row; p < p1; p += rows) {
-        float f[8];
-        unpack_bf16x8(ld_stream16(base + p * C), f);
+    for (int64_t p = p0 + row; p < p1; p += (int64_t)rows * GN_UNROLL) {
+        uint4 v[GN_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] += f[k] * f[k]; }
+        for (int u = 0; u < GN_UNROLL; ++u) {           // all loads first: GN_UNROLL x 16 B in flight per thread
+            const int64_t pp = p + (int64_t)u * rows;
+            v[u] = pp < p1 ? ld_stream16(base + pp * C) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+            float f[8];
+            unpack_bf16x8(v[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] += f[k] * f[k]; }
+        }
     }
     if (cpg >= 8) {
         float a = 0.f, q = 0.f;
@@ -111,15 +121,26 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
     const int64_t off = (int64_t)b * HW * C + col * 8;
-    for (int64_t p = p0 + row; p < p1; p += rows) {
-        float f[8];
-        unpack_bf16x8(ld_stream16(x + off + p * C), f);
+    for (int64_t p = p0 + row; p < p1; p += (int64_t)rows * GN_UNROLL) {
+        uint4 v[GN_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float v = f[k] * sc[k] + sh[k];
-            f[k] = SILU ? v * sigmoidf_fast(v) : v;
+        for (int u = 0; u < GN_UNROLL; ++u) {
+            const int64_t pp = p + (int64_t)u * rows;
+            v[u] = pp < p1 ? ld_stream16(x + off + pp * C) : make_uint4(0, 0, 0, 0);
         }
-        st_stream16(y + off + p * C, pack_bf16x8(f));
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+            const int64_t pp = p + (int64_t)u * rows;
+            if (pp >= p1) break;
+            float f[8];
+            unpack_bf16x8(v[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float t = f[k] * sc[k] + sh[k];
+                f[k] = SILU ? t * sigmoidf_fast(t) : t;
+            }
+            st_stream16(y + off + pp * C, pack_bf16x8(f));
+        }
     }
 }
 
@@ -150,20 +171,32 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
     const int64_t off = (int64_t)b * HW * C + col * 8;
-    for (int64_t p = p0 + row; p < p1; p += rows) {
-        float fx[8], fd[8];
-        unpack_bf16x8(ld_stream16(x + off + p * C), fx);
-        unpack_bf16x8(ld_stream16(da + off + p * C), fd);
+    constexpr int U = 2;
+    for (int64_t p = p0 + row; p < p1; p += (int64_t)rows * U) {
+        uint4 vx[U], vd[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float xh = (fx[k] - mean[k]) * rstd[k];
-            float dy = fd[k];
-            if (SILU) {
-                const float yv = xh * gm[k] + bt[k];
-                const float sg = sigmoidf_fast(yv);
-                dy *= sg * (1.f + yv * (1.f - sg));
+        for (int u = 0; u < U; ++u) {
+            const int64_t pp = p + (int64_t)u * rows;
+            const bool ok = pp < p1;
+            vx[u] = ok ? ld_stream16(x + off + pp * C) : make_uint4(0, 0, 0, 0);
+            vd[u] = ok ? ld_stream16(da + off + pp * C) : make_uint4(0, 0, 0, 0);     // da = 0 contributes nothing
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float fx[8], fd[8];
+            unpack_bf16x8(vx[u], fx);
+            unpack_bf16x8(vd[u], fd);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xh = (fx[k] - mean[k]) * rstd[k];
+                float dy = fd[k];
+                if (SILU) {
+                    const float yv = xh * gm[k] + bt[k];
+                    const float sg = sigmoidf_fast(yv);
+                    dy *= sg * (1.f + yv * (1.f - sg));
+                }
+                A[k] += dy; Bv[k] += dy * xh;
             }
-            A[k] += dy; Bv[k] += dy * xh;
         }
     }
 #pragma unroll
@@ -210,25 +243,38 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
     const int64_t off = (int64_t)b * HW * C + col * 8;
-    for (int64_t p = p0 + row; p < p1; p += rows) {
-        float fx[8], fd[8], fr[8];
-        unpack_bf16x8(ld_stream16(x + off + p * C), fx);
-        unpack_bf16x8(ld_stream16(da + off + p * C), fd);
-        if (dres) unpack_bf16x8(ld_stream16(dres + off + p * C), fr);
+    constexpr int U = 2;
+    for (int64_t p = p0 + row; p < p1; p += (int64_t)rows * U) {
+        uint4 vx[U], vd[U], vr[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float xh = (fx[k] - mean[k]) * rstd[k];
-            float dy = fd[k];
-            if (SILU) {
-                const float yv = xh * gm[k] + bt[k];
-                const float sg = sigmoidf_fast(yv);
-                dy *= sg * (1.f + yv * (1.f - sg));
-            }
-            float v = rstd[k] * (gm[k] * dy - m1[k] - xh * m2[k]);
-            if (dres) v += fr[k];
-            fx[k] = v;
+        for (int u = 0; u < U; ++u) {
+            const int64_t pp = p + (int64_t)u * rows;
+            const bool ok = pp < p1;
+            vx[u] = ok ? ld_stream16(x + off + pp * C) : make_uint4(0, 0, 0, 0);
+            vd[u] = ok ? ld_stream16(da + off + pp * C) : make_uint4(0, 0, 0, 0);
+            vr[u] = (ok && dres) ? ld_stream16(dres + off + pp * C) : make_uint4(0, 0, 0, 0);
         }
-        st_stream16(dx + off + p * C, pack_bf16x8(fx));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t pp = p + (int64_t)u * rows;
+            if (pp >= p1) break;
+            float fx[8], fd[8], fr[8];
+            unpack_bf16x8(vx[u], fx);
+            unpack_bf16x8(vd[u], fd);
+            unpack_bf16x8(vr[u], fr);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xh = (fx[k] - mean[k]) * rstd[k];
+                float dy = fd[k];
+                if (SILU) {
+                    const float yv = xh * gm[k] + bt[k];
+                    const float sg = sigmoidf_fast(yv);
+                    dy *= sg * (1.f + yv * (1.f - sg));
+                }
+                fx[k] = rstd[k] * (gm[k] * dy - m1[k] - xh * m2[k]) + fr[k];
+            }
+            st_stream16(dx + off + pp * C, pack_bf16x8(fx));
+        }
     }
 }
 

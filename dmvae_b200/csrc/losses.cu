@@ -134,15 +134,16 @@ __global__ void __launch_bounds__(256) dmd_loss_kernel(
     TD* __restrict__ dz, double* __restrict__ acc, int64_t P, float cfg_m1, int use_cfg, int normalize,
     float dz_scale) {
     constexpr int VN = VEC ? Vec<T>::N : 1;
-    extern __shared__ float dyn[];
+    // z and the numerator are values of type T (already rounded), so the cache holds them as T: 4 B/element for bf16
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
     __shared__ float red[64];
     __shared__ float s_w;
     const int64_t b = blockIdx.x;
     const int64_t base = b * P;
     const float tb = ld_as_float(t, b);
     const float omt = rnd<T>(__fsub_rn(1.f, tb));
-    float* s_z = dyn;
-    float* s_d = dyn + (CACHE ? P : 0);
+    T* s_z = reinterpret_cast<T*>(dyn_raw);
+    T* s_d = s_z + (CACHE ? P : 0);
     const int64_t nv = P / VN;
 
     float v[1] = {0.f};
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) dmd_loss_kernel(
 #pragma unroll
         for (int k = 0; k < VN; ++k) {
             v[0] += fabsf(pr[k]);
-            if (CACHE) { s_z[j * VN + k] = zf[k]; s_d[j * VN + k] = df[k]; }
+            if (CACHE) { st_from_float(s_z, j * VN + k, zf[k]); st_from_float(s_d, j * VN + k, df[k]); }
         }
     }
     block_sum<1>(v, red);
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) dmd_loss_kernel(
         float zf[VN], df[VN], o[VN];
         if (CACHE) {
 #pragma unroll
-            for (int k = 0; k < VN; ++k) { zf[k] = s_z[j * VN + k]; df[k] = s_d[j * VN + k]; }
+            for (int k = 0; k < VN; ++k) { zf[k] = ld_as_float(s_z, j * VN + k); df[k] = ld_as_float(s_d, j * VN + k); }
         } else {
             float pr[VN];
             dmd_load<T, VEC>(z, xt, vTc, vTu, vSc, vSu, base + j * VN, omt, cfg_m1, use_cfg, zf, pr, df);
@@ -196,7 +197,7 @@ template <typename T, typename TD, bool VEC>
 static int launch_dmd_v(const void* z, const void* xt, const void* t, const void* vTc, const void* vTu,
                         const void* vSc, const void* vSu, void* dz, double* acc, int64_t B, int64_t P,
                         float cfg_m1, int use_cfg, int normalize, float dz_scale, cudaStream_t st) {
-    const size_t cache_bytes = (size_t)P * 2 * sizeof(float);
+    const size_t cache_bytes = (size_t)P * 2 * sizeof(T);
     if (cache_bytes <= 96 * 1024) {
         auto k = dmd_loss_kernel<T, TD, true, VEC>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

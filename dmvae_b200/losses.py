@@ -41,8 +41,9 @@ class _DmdLossFn(torch.autograd.Function):
         t = t.detach().to(dt).contiguous()
         dz = torch.empty(zc.shape, dtype=dz_dtype, device=zc.device)
         acc = torch.zeros(2, dtype=torch.float64, device=zc.device)
-        call("dmvae_dmd_loss_fwd_bwd", ptr(zc), ptr(xt), ptr(t), ptr(vT_c), ptr(vT_u), ptr(vS_c), ptr(vS_u), ptr(dz), ptr(acc),
-             B, P, float(cfg_scale), int(normalize), 1.0, dtype_code(zc), dtype_code(dz))
+        if B * P > 0:                     # empty batch: nothing to launch (an empty tensor's data_ptr() is NULL)
+            call("dmvae_dmd_loss_fwd_bwd", ptr(zc), ptr(xt), ptr(t), ptr(vT_c), ptr(vT_u), ptr(vS_c), ptr(vS_u), ptr(dz),
+                 ptr(acc), B, P, float(cfg_scale), int(normalize), 1.0, dtype_code(zc), dtype_code(dz))
         n = max(B * P, 1)
         loss = (acc[0] * (0.5 / n)).float()
         gnorm = (acc[1] / max(B, 1)).float()

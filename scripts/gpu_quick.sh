@@ -1,0 +1,19 @@
+#!/bin/bash
+# parity + bench + microbench, no ncu
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps ${STEPS:-10} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench rc=$?" >> gpurun_out/bench.err
+timeout 600 python scripts/microbench.py --iters 10 ${MICRO_ARGS} > gpurun_out/micro.jsonl 2> gpurun_out/micro.err
+tail -n 5 gpurun_out/pytest_gpu.log; tail -n 3 gpurun_out/bench.err
+python - <<'PY'
+import json
+try:
+    d=json.load(open('gpurun_out/bench.json'))
+    print('value',d['value'],'e2e',d['e2e']['value'],'ms/step',d['ms_per_step'],'roof',d['roofline']['achieved'],d['roofline']['frac'],'wgrad',d['wgrad'])
+    for k,v in d['kernels_ms_per_step'].items(): print('  ',k,v)
+except Exception as e: print('bench parse failed',e)
+for l in open('gpurun_out/micro.jsonl'):
+    d=json.loads(l); print(d['kernel'],d['shape'],d['us'],'us',d['frac_of_hbm_peak'])
+PY
