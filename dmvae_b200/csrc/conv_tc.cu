@@ -123,20 +123,26 @@ struct TcGeom {
     int m_tiles, n_tiles, k_chunks;
 };
 
-template <int BN> struct Cfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int A_BYTES = BM * BK * 2;
+// MT = 128-pixel sub-tiles per CTA.  MT = 2 halves the L2->SM operand traffic per FLOP (one weight tile feeds two
+// pixel tiles: 64 B/cycle/SM instead of 94-128), which is what bounds the 128-pixel tile (ncu: tensor pipe 45 % active).
+template <int BN, int MT> struct Cfg {
+    static constexpr int A_BYTES = MT * BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers (64, 256 or 512 columns)
+    static constexpr int ACC_COLS = MT * BN;                             // one accumulator set
+    static constexpr int NBUF = (2 * ACC_COLS <= 512) ? 2 : 1;           // double-buffer when TMEM allows
+    static constexpr uint32_t TMEM_COLS = (NBUF * ACC_COLS < 32) ? 32 : NBUF * ACC_COLS;
+    static constexpr int EPI_WARPS = 4 * MT;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int MT>
+__global__ void __launch_bounds__(Cfg<BN, MT>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out, TcGeom g) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -154,7 +160,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         prefetch_tmap(&map_a);
         prefetch_tmap(&map_b);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], C::EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -178,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         uint8_t* sa = smem + stage * C::STAGE_BYTES;
                         uint8_t* sb = sa + C::A_BYTES;
                         mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-                        tma_load_4d(sa, &map_a, &full[stage], kc * BK, w0 + kw, h0 + kh, b);
+                        tma_load_4d(sa, &map_a, &full[stage], kc * BK, w0 + kw, h0 + kh, b);   // MT*128 pixels x 64 ch
                         tma_load_3d(sb, &map_b, &full[stage], kc * BK, n0, tap);
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -192,42 +198,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                const int buf = (C::NBUF == 2) ? (it & 1) : 0;
+                const uint32_t par = (C::NBUF == 2) ? ((it >> 1) & 1) : (it & 1);
+                mbar_wait(&tempty[buf], par ^ 1);                   // epilogue has drained this accumulator set
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * BN;
+                const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
                 for (int k = 0; k < k_iters; ++k) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
                     const uint64_t bdesc = make_kmajor_sw128_desc(sa + C::A_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                        // advance 16 elements (32 B) along K inside the swizzled row: +2 in 16-byte units
-                        umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+                    for (int sub = 0; sub < MT; ++sub) {
+                        const uint64_t adesc = make_kmajor_sw128_desc(sa + sub * (BM * BK * 2));
+#pragma unroll
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            // advance 16 elements (32 B) along K inside the swizzled row: +2 in 16-byte units
+                            umma_bf16(d_tmem + sub * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+                        }
                     }
                     umma_commit(&empty[stage]);                     // frees the smem slot when these MMAs retire
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[buf]);                           // accumulator complete -> epilogue
+                umma_commit(&tfull[buf]);                           // accumulators complete -> epilogue
             }
         }
     } else {
-        // ============================== epilogue (warps 2..5) ==============================
+        // ============================== epilogue (warps 2 .. 2+4*MT) ==============================
         const int lg = warp & 3;                 // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
-        const int r = lg * 32 + lane;            // row of the tile = pixel index inside the tile
+        const int sub = (warp - 2) >> 2;         // which 128-pixel sub-tile
+        const int r = sub * BM + lg * 32 + lane; // row of the tile = pixel index inside the tile
         const int dh = r / g.BW, dw = r % g.BW;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
+            const int buf = (C::NBUF == 2) ? (it & 1) : 0;
+            const uint32_t par = (C::NBUF == 2) ? ((it >> 1) & 1) : (it & 1);
             const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
             const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
             const int64_t pix = ((int64_t)b * g.H + th * g.BH + dh) * g.W + tw * g.BW + dw;
             const int n0 = nt * BN;
-            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            mbar_wait(&tfull[buf], par);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * C::ACC_COLS + sub * BN;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
@@ -486,20 +498,30 @@ int get_tensor_map(const void* ptr, int rank, const uint64_t* dims, const uint32
     return DMVAE_OK;
 }
 
-int pick_pixel_tile(int H, int W, int* BW, int* BH) {
+int pick_pixel_tile_n(int H, int W, int pixels, int* BW, int* BH) {
     int bw = 1;
-    while (bw * 2 <= 128 && W % (bw * 2) == 0) bw *= 2;
-    const int bh = BM / bw;
+    while (bw * 2 <= pixels && bw * 2 <= 256 && W % (bw * 2) == 0) bw *= 2;
+    const int bh = pixels / bw;
     if (bw < 8 || H % bh != 0 || bh > 256) return 0;
     *BW = bw; *BH = bh;
     return 1;
 }
+int pick_pixel_tile(int H, int W, int* BW, int* BH) { return pick_pixel_tile_n(H, W, BM, BW, BH); }
 
 int g_num_sms = 0;
+int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
 
-template <int BN>
+template <int BN, int MT>
 int launch_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, TcGeom g, cudaStream_t st) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, MT>;
     CUtensorMap ma, mb;
     const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
     const uint32_t abox[4] = {BK, (uint32_t)g.BW, (uint32_t)g.BH, 1};
@@ -511,22 +533,19 @@ int launch_conv_tc(const void* x, const void* w, const float* bias, const void* 
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return dmvae_set_error(DMVAE_ECUDA, "conv_tc: smem attribute: %s", cudaGetErrorString(e));
         attr_done = true;
     }
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
     const int tiles = g.m_tiles * g.n_tiles;
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, g);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    conv_tc_kernel<BN, MT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, g);
     DMVAE_CHECK_LAUNCH("conv_tc_kernel");
     return DMVAE_OK;
 }
+
+// 0 = let the heuristic decide, 1 / 2 = force the number of 128-pixel sub-tiles per CTA (tests, tuning)
+int g_force_mt = 0;
 
 }  // namespace
 
@@ -551,21 +570,26 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     TcGeom g;
     g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
     g.pt = (KH - 1) / 2; g.pl = (KW - 1) / 2;
-    pick_pixel_tile(H, W, &g.BW, &g.BH);
-    g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
-    g.m_tiles = B * g.tiles_w * g.tiles_h;
     g.k_chunks = (Cin + BK - 1) / BK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cout <= 32) {
-        g.n_tiles = 1;
-        return launch_conv_tc<32>(x, w_packed, bias, residual, y, g, st);
+    const int bn = Cout <= 32 ? 32 : ((Cout % 256 == 0 || Cout > 256) ? 256 : 128);
+    g.n_tiles = (Cout + bn - 1) / bn;
+    // 256-pixel tiles when the image allows them and there is at least ~one wave of them
+    int mt = 1, bw2, bh2;
+    if (bn >= 128 && pick_pixel_tile_n(H, W, 2 * BM, &bw2, &bh2)) {
+        const int tiles2 = B * (W / bw2) * (H / bh2) * g.n_tiles;
+        if (tiles2 >= (num_sms() * 3) / 4) mt = 2;
     }
-    if (Cout % 256 == 0 || Cout > 256) {
-        g.n_tiles = (Cout + 255) / 256;
-        return launch_conv_tc<256>(x, w_packed, bias, residual, y, g, st);
-    }
-    g.n_tiles = (Cout + 127) / 128;
-    return launch_conv_tc<128>(x, w_packed, bias, residual, y, g, st);
+    if (g_force_mt == 1) mt = 1;
+    if (g_force_mt == 2 && bn >= 128 && pick_pixel_tile_n(H, W, 2 * BM, &bw2, &bh2)) mt = 2;
+    pick_pixel_tile_n(H, W, mt * BM, &g.BW, &g.BH);
+    g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
+    g.m_tiles = B * g.tiles_w * g.tiles_h;
+    if (bn == 32) return launch_conv_tc<32, 1>(x, w_packed, bias, residual, y, g, st);
+    if (bn == 256) return mt == 2 ? launch_conv_tc<256, 2>(x, w_packed, bias, residual, y, g, st)
+                                  : launch_conv_tc<256, 1>(x, w_packed, bias, residual, y, g, st);
+    return mt == 2 ? launch_conv_tc<128, 2>(x, w_packed, bias, residual, y, g, st)
+                   : launch_conv_tc<128, 1>(x, w_packed, bias, residual, y, g, st);
 }
 
 namespace {
@@ -634,4 +658,10 @@ DMVAE_API int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_m
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin >= 256) return launch_wgrad_tc<256>(x, dy, dw_tap_major, g, st);
     return launch_wgrad_tc<128>(x, dy, dw_tap_major, g, st);
+}
+
+// test / tuning hook: 0 = heuristic, 1 = 128-pixel tiles, 2 = 256-pixel tiles where the shape allows
+DMVAE_API int dmvae_conv_tc_set_tile_mode(int mode) {
+    g_force_mt = (mode == 1 || mode == 2) ? mode : 0;
+    return DMVAE_OK;
 }

@@ -74,7 +74,8 @@ class _L1L2Fn(torch.autograd.Function):
         x = image.detach().float().contiguous()
         acc = torch.zeros(2, dtype=torch.float64, device=r.device)
         n = r.numel()
-        call("dmvae_l1l2_fwd", ptr(r), ptr(x), ptr(acc), n)
+        if n:
+            call("dmvae_l1l2_fwd", ptr(r), ptr(x), ptr(acc), n)
         out = (acc / max(n, 1)).float()
         ctx.save_for_backward(r, x)
         return out[0], out[1]
@@ -85,7 +86,8 @@ class _L1L2Fn(torch.autograd.Function):
         d = torch.empty_like(r)
         g1 = g1.float().contiguous()
         g2 = g2.float().contiguous()
-        call("dmvae_l1l2_bwd", ptr(r), ptr(x), ptr(d), ptr(g1), ptr(g2), r.numel(), 1.0, 1.0)
+        if r.numel():
+            call("dmvae_l1l2_bwd", ptr(r), ptr(x), ptr(d), ptr(g1), ptr(g2), r.numel(), 1.0, 1.0)
         return d, None
 
 
@@ -101,7 +103,8 @@ def l1l2_fused(recon: torch.Tensor, image: torch.Tensor, w_l1: float, w_l2: floa
     acc = torch.zeros(2, dtype=torch.float64, device=r.device)
     d = torch.empty_like(r)
     n = r.numel()
-    call("dmvae_l1l2_fwd_bwd", ptr(r), ptr(x), ptr(d), ptr(acc), n, float(w_l1), float(w_l2))
+    if n:
+        call("dmvae_l1l2_fwd_bwd", ptr(r), ptr(x), ptr(d), ptr(acc), n, float(w_l1), float(w_l2))
     out = (acc / max(n, 1)).float()
     return out[0], out[1], d
 

@@ -117,6 +117,9 @@ int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int 
 int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
                       int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
 
+/* Tuning / test hook (host only): 0 = heuristic, 1 = 128-pixel tiles per CTA, 2 = 256-pixel tiles where possible. */
+int dmvae_conv_tc_set_tile_mode(int mode);
+
 /* tcgen05 weight gradient (both operands MN-major): dw_tap_major[tap][Cout][Cin] (fp32, caller-zeroed or
  * accumulated) += sum_pixels dy[p][co] * x[p(+)tap][ci].  Replaces cuDNN backward-filter for the same call sites.
  * dmvae_wgrad_unpack moves the tap-major scratch into the state_dict layout dw[Cout][Cin][KH][KW]. */

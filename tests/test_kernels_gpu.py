@@ -282,6 +282,23 @@ def test_conv_tcgen05(case):
     _conv_case(*case, force_direct=False)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("case", [
+    (2, 128, 128, 16, 16, 3, 1, (1, 1), True),    # BN=128: one 256-pixel tile per image
+    (1, 512, 512, 32, 32, 3, 1, (1, 1), True),    # BN=256, single TMEM accumulator set when MT=2
+    (3, 64, 256, 8, 64, 1, 1, (0, 0), False),
+    (2, 128, 128, 2, 256, 3, 1, (1, 1), False),   # W=256: a 256-pixel tile is one image row
+])
+def test_conv_tcgen05_tile_modes(case, mode):
+    """Both CTA tile shapes (128 or 256 pixels per CTA) must give the same answers."""
+    from dmvae_b200 import _lib
+    _lib.query("dmvae_conv_tc_set_tile_mode", mode)
+    try:
+        _conv_case(*case, force_direct=False, seed=mode)
+    finally:
+        _lib.query("dmvae_conv_tc_set_tile_mode", 0)
+
+
 def test_conv_tc_many_tiles_matches_direct():
     """Full-size layer (512->512 @64x64, B=2: 128 pixel tiles x 2 N tiles): tensor-core path vs CUDA-core path on device."""
     ops, _ = _ops()
