@@ -144,29 +144,45 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
     }
 }
 
-// Backward, pass 1.  dy = da * swish'(y).  Per channel: A_c = sum dy, B_c = sum dy * xhat.
-//   dbeta_c += A_c ; dgamma_c += B_c ; gsum[b][g] += {sum_c gamma_c A_c, sum_c gamma_c B_c}
+// Backward.  With y = a_c x + b_c (a = rstd*gamma, b = beta - mean*a) and xhat = r x + s (r = rstd, s = -mean*rstd):
+//   dy = da * swish'(y),  swish'(y) = sg + y sg (1 - sg)
+// pass 1 (reduce):  A_c = sum dy, B_c = sum dy*xhat ;  dbeta += A, dgamma += B, gsum[b][g] += {sum gamma A, sum gamma B}
+// pass 2 (apply):   dx = rstd*(gamma*dy - (S1 + xhat*S2)/n) [+ dres] = a*dy + k0 + k1*x [+ dres]
+//                   k1 = -rstd^2 * S2/n,  k0 = -rstd*(S1/n + s*S2/n)
+// Per-channel coefficients are folded once per CTA so the per-element work is ~16 instructions and the register
+// footprint allows 3 CTAs per SM.
 template <bool SILU>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(
+__device__ __forceinline__ float gn_dy(float da, float yv) {
+    if (!SILU) return da;
+    const float sg = sigmoidf_fast(yv);
+    return da * fmaf(yv * sg, 1.f - sg, sg);
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(
     const bf16* __restrict__ da, const bf16* __restrict__ x, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ gsum,
     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t HW, int C, int vc, int rows, int64_t ppb, float eps) {
-    extern __shared__ float s_mem[];   // mean[C] rstd[C] accA[C] accB[C]
-    float* s_mean = s_mem; float* s_rstd = s_mem + C; float* s_A = s_mem + 2 * C; float* s_B = s_mem + 3 * C;
+    extern __shared__ float s_mem[];   // a[C] b[C] r[C] s[C] accA[C] accB[C]
+    float* s_a = s_mem; float* s_b = s_mem + C; float* s_r = s_mem + 2 * C; float* s_s = s_mem + 3 * C;
+    float* s_A = s_mem + 4 * C; float* s_B = s_mem + 5 * C;
     const int b = blockIdx.y;
     const int cpg = C / GN_GROUPS;
     const double n = (double)HW * cpg;
     for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-        gn_mean_rstd(stats, b, c / cpg, n, eps, s_mean[c], s_rstd[c]);
+        float mean, rstd;
+        gn_mean_rstd(stats, b, c / cpg, n, eps, mean, rstd);
+        const float a = rstd * gamma[c];
+        s_a[c] = a; s_b[c] = beta[c] - mean * a; s_r[c] = rstd; s_s[c] = -mean * rstd;
         s_A[c] = 0.f; s_B[c] = 0.f;
     }
     __syncthreads();
     const int col = threadIdx.x % vc, row = threadIdx.x / vc;
-    float mean[8], rstd[8], gm[8], bt[8], A[8], Bv[8];
+    float ca[8], cb[8], cr[8], cs[8], A[8], Bv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = col * 8 + k;
-        mean[k] = s_mean[c]; rstd[k] = s_rstd[c]; gm[k] = gamma[c]; bt[k] = beta[c]; A[k] = 0.f; Bv[k] = 0.f;
+        ca[k] = s_a[c]; cb[k] = s_b[c]; cr[k] = s_r[c]; cs[k] = s_s[c]; A[k] = 0.f; Bv[k] = 0.f;
     }
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
@@ -188,14 +204,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(
             unpack_bf16x8(vd[u], fd);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float xh = (fx[k] - mean[k]) * rstd[k];
-                float dy = fd[k];
-                if (SILU) {
-                    const float yv = xh * gm[k] + bt[k];
-                    const float sg = sigmoidf_fast(yv);
-                    dy *= sg * (1.f + yv * (1.f - sg));
-                }
-                A[k] += dy; Bv[k] += dy * xh;
+                const float dy = gn_dy<SILU>(fd[k], fmaf(fx[k], ca[k], cb[k]));
+                A[k] += dy;
+                Bv[k] = fmaf(dy, fmaf(fx[k], cr[k], cs[k]), Bv[k]);
             }
         }
     }
@@ -215,30 +226,34 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(
     }
 }
 
-// Backward, pass 2.  dx = rstd * (gamma*dy - (S1 + xhat*S2)/n) [+ dres]
 template <bool SILU>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
     const bf16* __restrict__ da, const bf16* __restrict__ x, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ gsum,
     const bf16* __restrict__ dres, bf16* __restrict__ dx, int64_t HW, int C, int vc, int rows, int64_t ppb, float eps) {
-    extern __shared__ float s_mem[];   // mean[C] rstd[C] m1[C] m2[C]
-    float* s_mean = s_mem; float* s_rstd = s_mem + C; float* s_m1 = s_mem + 2 * C; float* s_m2 = s_mem + 3 * C;
+    extern __shared__ float s_mem[];   // a[C] b[C] k0[C] k1[C]
+    float* s_a = s_mem; float* s_b = s_mem + C; float* s_k0 = s_mem + 2 * C; float* s_k1 = s_mem + 3 * C;
     const int b = blockIdx.y;
     const int cpg = C / GN_GROUPS;
     const double n = (double)HW * cpg;
     for (int c = threadIdx.x; c < C; c += GN_THREADS) {
         const int g = c / cpg;
-        gn_mean_rstd(stats, b, g, n, eps, s_mean[c], s_rstd[c]);
-        s_m1[c] = (float)(gsum[((int64_t)b * GN_GROUPS + g) * 2] / n);
-        s_m2[c] = (float)(gsum[((int64_t)b * GN_GROUPS + g) * 2 + 1] / n);
+        float mean, rstd;
+        gn_mean_rstd(stats, b, g, n, eps, mean, rstd);
+        const float m1 = (float)(gsum[((int64_t)b * GN_GROUPS + g) * 2] / n);
+        const float m2 = (float)(gsum[((int64_t)b * GN_GROUPS + g) * 2 + 1] / n);
+        const float a = rstd * gamma[c];
+        s_a[c] = a; s_b[c] = beta[c] - mean * a;
+        s_k1[c] = -rstd * rstd * m2;
+        s_k0[c] = -rstd * (m1 - mean * rstd * m2);
     }
     __syncthreads();
     const int col = threadIdx.x % vc, row = threadIdx.x / vc;
-    float mean[8], rstd[8], gm[8], bt[8], m1[8], m2[8];
+    float ca[8], cb[8], k0[8], k1[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = col * 8 + k;
-        mean[k] = s_mean[c]; rstd[k] = s_rstd[c]; gm[k] = gamma[c]; bt[k] = beta[c]; m1[k] = s_m1[c]; m2[k] = s_m2[c];
+        ca[k] = s_a[c]; cb[k] = s_b[c]; k0[k] = s_k0[c]; k1[k] = s_k1[c];
     }
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
@@ -264,14 +279,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
             unpack_bf16x8(vr[u], fr);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float xh = (fx[k] - mean[k]) * rstd[k];
-                float dy = fd[k];
-                if (SILU) {
-                    const float yv = xh * gm[k] + bt[k];
-                    const float sg = sigmoidf_fast(yv);
-                    dy *= sg * (1.f + yv * (1.f - sg));
-                }
-                fx[k] = rstd[k] * (gm[k] * dy - m1[k] - xh * m2[k]) + fr[k];
+                const float dy = gn_dy<SILU>(fd[k], fmaf(fx[k], ca[k], cb[k]));
+                fx[k] = fmaf(ca[k], dy, fmaf(k1[k], fx[k], k0[k])) + fr[k];
             }
             st_stream16(dx + off + pp * C, pack_bf16x8(fx));
         }
@@ -327,13 +336,14 @@ DMVAE_API int dmvae_gn_bwd(const void* da, const void* x, const double* stats, c
     dim3 grid; int64_t ppb;
     gn_grid(B, HW, g.rows, &grid, &ppb);
     const size_t smem = (size_t)4 * C * sizeof(float);
+    const size_t smem_r = (size_t)6 * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     if (silu) {
-        gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
+        gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem_r, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
         DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");
         gn_bwd_apply_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, HW, C, g.vc, g.rows, ppb, eps);
     } else {
-        gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
+        gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem_r, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
         DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");
         gn_bwd_apply_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, HW, C, g.vc, g.rows, ppb, eps);
     }

@@ -15,5 +15,5 @@ try:
     for k,v in d['kernels_ms_per_step'].items(): print('  ',k,v)
 except Exception as e: print('bench parse failed',e)
 for l in open('gpurun_out/micro.jsonl'):
-    d=json.loads(l); print(d['kernel'],d['shape'],d['us'],'us',d['frac_of_hbm_peak'])
+    d=json.loads(l); print(' '.join(f'{k}={v}' for k,v in d.items() if k!='algo_bytes'))
 PY

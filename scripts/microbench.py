@@ -77,6 +77,30 @@ def main():
         del xs, das, stats
         torch.cuda.empty_cache()
 
+    if want("convtc"):
+        from dmvae_b200 import _lib
+        shapes = [(512, 512, 32, 3), (512, 512, 64, 3), (512, 512, 128, 3), (512, 256, 128, 3), (256, 256, 128, 3), (256, 256, 256, 3),
+                  (256, 128, 256, 3), (128, 128, 256, 3), (512, 512, 32, 1), (512, 256, 128, 1), (256, 128, 256, 1), (32, 512, 32, 3)]
+        for cin, cout, hw, k in shapes:
+            B = 16
+            x = torch.randn(B, hw, hw, cin, device=DEV).bfloat16()
+            dy = torch.randn(B, hw, hw, cout, device=DEV).bfloat16()
+            w = torch.randn(cout, cin, k, k, device=DEV) * 0.02
+            bias = torch.zeros(cout, device=DEV)
+            wf, wd = ops.WeightPack().get(w)
+            flops = 2.0 * B * hw * hw * cin * cout * k * k
+            res = {}
+            for mode in (1, 2):
+                _lib.query("dmvae_conv_tc_set_tile_mode", mode)
+                us = timeit(lambda i: ops.conv_forward_raw(x, wf, bias, None, k, k, 1, ((k - 1) // 2, (k - 1) // 2)), a.iters, 1)
+                res[f"fwd_mt{mode}_tflops"] = round(flops / us / 1e6, 1)
+            _lib.query("dmvae_conv_tc_set_tile_mode", 0)
+            us = timeit(lambda i: ops.conv_wgrad_raw(x, dy, k, k, 1, ((k - 1) // 2, (k - 1) // 2)), a.iters, 1)
+            res["wgrad_tflops"] = round(flops / us / 1e6, 1)
+            print(json.dumps({"kernel": "conv_tc", "cin": cin, "cout": cout, "hw": hw, "k": k, "gflop": round(flops / 1e9, 1), **res}), flush=True)
+            del x, dy
+            torch.cuda.empty_cache()
+
     if want("conv_out"):
         shp = (16, 256, 256, 128)
         x = torch.randn(shp, device=DEV).bfloat16()

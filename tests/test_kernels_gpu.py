@@ -121,7 +121,7 @@ def test_lpips_distance(dtype, c, hw):
     f0 = torch.relu(torch.randn(2, c, hw, hw, generator=g)).to(dtype)
     f1 = torch.relu(torch.randn(2, c, hw, hw, generator=g)).to(dtype)
     w = torch.rand(c, generator=g)
-    f1r = f1.float().requires_grad_(True)
+    f1r = f1.float().clone().requires_grad_(True)
     ref = O.lpips_distance([f0], [f1r], [w])
     ref.backward()
     f1c = f1.to(DEV).requires_grad_(True)
@@ -151,7 +151,7 @@ def test_reparam_kl(dtype):
     g = torch.Generator().manual_seed(4)
     h = (torch.randn(3, 8, 4, 4, generator=g) * 0.5).to(dtype)
     eps = torch.randn(3, 4, 4, 4, generator=g).to(dtype)
-    hr = h.float().requires_grad_(True)
+    hr = h.float().clone().requires_grad_(True)
     mu, lv = hr.chunk(2, dim=1)
     z_ref, kl_ref = O.reparam_kl(mu, lv, eps)
     (z_ref.sum() * 0.3 + kl_ref * 0.01).backward()
