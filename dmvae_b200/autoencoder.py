@@ -52,8 +52,8 @@ class _PackMixin:
         return new
 
 
-def _conv(mod: "_PackMixin", name: str, conv: nn.Conv2d, x_cl: Tensor, stride=1, pad_tl=(1, 1), residual=None) -> Tensor:
-    return ops.conv2d(x_cl, conv.weight, conv.bias, mod._pack(name), stride, pad_tl, residual)
+def _conv(mod: "_PackMixin", name: str, conv: nn.Conv2d, x_cl: Tensor, stride=1, pad_tl=(1, 1), residual=None, pad_br=None) -> Tensor:
+    return ops.conv2d(x_cl, conv.weight, conv.bias, mod._pack(name), stride, pad_tl, residual, pad_br)
 
 
 def _gn(norm: nn.GroupNorm, x_cl: Tensor, silu: bool) -> Tensor:
@@ -120,7 +120,7 @@ class Downsample(_PackMixin, nn.Module):
         self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
 
     def _forward_cl(self, x: Tensor) -> Tensor:
-        return _conv(self, "conv", self.conv, x, 2, (0, 0))
+        return _conv(self, "conv", self.conv, x, 2, (0, 0), pad_br=(1, 1))
 
     def forward(self, x: Tensor):
         return _from_cl(self._forward_cl(_to_cl(x)))

@@ -59,14 +59,17 @@ class WeightPack:
 # ------------------------------------------------------------------------------------------------ raw kernels
 def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
                      kh: int, kw: int, stride: int = 1, pad_tl: Tuple[int, int] = (1, 1),
-                     out_hw: Optional[Tuple[int, int]] = None, force_direct: bool = False) -> torch.Tensor:
-    """y = conv(x, w_packed[tap][Cout][Cin]) + bias (+ residual).  Picks the tcgen05 tile when the shape allows."""
+                     out_hw: Optional[Tuple[int, int]] = None, force_direct: bool = False,
+                     pad_br: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """y = conv(x, w_packed[tap][Cout][Cin]) + bias (+ residual).  Picks the tcgen05 tile when the shape allows.
+    pad_tl / pad_br: zero padding (top, left) / (bottom, right); pad_br defaults to pad_tl."""
     B, H, W, cin = x.shape
     taps, cout, cin_w = w_packed.shape
     assert taps == kh * kw and cin_w == cin, (w_packed.shape, x.shape, kh, kw)
     pt, pl = pad_tl
     if out_hw is None:
-        out_hw = ((H + 2 * pt - kh) // stride + 1, (W + 2 * pl - kw) // stride + 1)
+        pb, pr = pad_tl if pad_br is None else pad_br
+        out_hw = ((H + pt + pb - kh) // stride + 1, (W + pl + pr - kw) // stride + 1)
     OH, OW = out_hw
     y = torch.empty((B, OH, OW, cout), dtype=torch.bfloat16, device=x.device)
     if bias is not None and bias.dtype != torch.float32:
@@ -149,13 +152,13 @@ class ConvFn(torch.autograd.Function):
     """nn.Conv2d on channels-last bf16 (models/flux_ae.py:32-35,63,65,67,89,101,133,158,210,237,274)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, pack: WeightPack, stride: int, pad_tl):
+    def forward(ctx, x, weight, bias, residual, pack: WeightPack, stride: int, pad_tl, pad_br=None):
         x = _chk_nhwc(x, "conv")
         cout, cin, kh, kw = weight.shape
         w_fwd, w_dgrad = pack.get(weight)
         if residual is not None:
             residual = _chk_nhwc(residual, "conv residual")
-        y = conv_forward_raw(x, w_fwd, None if bias is None else bias.detach(), residual, kh, kw, stride, pad_tl)
+        y = conv_forward_raw(x, w_fwd, None if bias is None else bias.detach(), residual, kh, kw, stride, pad_tl, pad_br=pad_br)
         ctx.geom = (kh, kw, stride, pad_tl, x.shape[1:3])
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
@@ -176,7 +179,7 @@ class ConvFn(torch.autograd.Function):
             db = bias_grad_raw(dy)
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
-        return dx, dw, db, dres, None, None, None
+        return dx, dw, db, dres, None, None, None, None
 
 
 class GroupNormSiluFn(torch.autograd.Function):
@@ -265,8 +268,8 @@ class ToNchwFn(torch.autograd.Function):
         return dx, None
 
 
-def conv2d(x, weight, bias, pack: WeightPack, stride: int = 1, pad_tl=(1, 1), residual=None):
-    return ConvFn.apply(x, weight, bias, residual, pack, stride, pad_tl)
+def conv2d(x, weight, bias, pack: WeightPack, stride: int = 1, pad_tl=(1, 1), residual=None, pad_br=None):
+    return ConvFn.apply(x, weight, bias, residual, pack, stride, pad_tl, pad_br)
 
 
 def group_norm_silu(x, gamma, beta, silu: bool = True):

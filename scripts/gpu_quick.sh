@@ -1,7 +1,7 @@
 #!/bin/bash
 # parity + bench + microbench, no ncu
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps ${STEPS:-10} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench rc=$?" >> gpurun_out/bench.err
@@ -17,3 +17,8 @@ except Exception as e: print('bench parse failed',e)
 for l in open('gpurun_out/micro.jsonl'):
     d=json.loads(l); print(' '.join(f'{k}={v}' for k,v in d.items() if k!='algo_bytes'))
 PY
+if [ "${PROFILE_STEP:-0}" = "1" ]; then
+  timeout 600 python scripts/profile_step.py > gpurun_out/step_profile.txt 2>&1
+  head -75 gpurun_out/step_profile.txt | cut -c1-200
+fi
+grep -E "^FAILED|^ERROR" gpurun_out/pytest_gpu.log | head -20

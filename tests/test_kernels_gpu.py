@@ -235,7 +235,7 @@ def _conv_case(B, cin, cout, H, W, k, stride, pad_tl, residual, force_direct, se
     wf, wd = pack.get(w.to(DEV))
     xc = nhwc(x)
     y = ops.conv_forward_raw(xc, wf, None if b is None else b.to(DEV), None if res is None else nhwc(res), k, k, stride, pad_tl,
-                             force_direct=force_direct)
+                             force_direct=force_direct, pad_br=(1, 1) if stride == 2 else None)
     dyc = nhwc(dy)
     dx = ops.conv_dgrad_raw(dyc, wf, wd, (H, W), k, k, stride, pad_tl, force_direct=force_direct)
     dw = ops.conv_wgrad_raw(xc, dyc, k, k, stride, pad_tl, force_direct=force_direct)
