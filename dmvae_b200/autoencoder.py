@@ -77,11 +77,11 @@ class AttnBlock(_PackMixin, nn.Module):
     def _forward_cl(self, x: Tensor) -> Tensor:
         B, H, W, c = x.shape
         h = _gn(self.norm, x, False)
-        q = _conv(self, "q", self.q, h, 1, (0, 0)).view(B, 1, H * W, c)     # "b c h w -> b 1 (h w) c" is free here
-        k = _conv(self, "k", self.k, h, 1, (0, 0)).view(B, 1, H * W, c)
-        v = _conv(self, "v", self.v, h, 1, (0, 0)).view(B, 1, H * W, c)
-        o = nn.functional.scaled_dot_product_attention(q, k, v)             # single head, d = C (library op, 0.3% of FLOPs)
-        o = o.reshape(B, H, W, c).to(torch.bfloat16)
+        q = _conv(self, "q", self.q, h, 1, (0, 0)).view(B, H * W, c)        # "b c h w -> b 1 (h w) c" is free here
+        k = _conv(self, "k", self.k, h, 1, (0, 0)).view(B, H * W, c)
+        v = _conv(self, "v", self.v, h, 1, (0, 0)).view(B, H * W, c)
+        o = ops.single_head_attention(q, k, v)                              # single head, d = C (library GEMMs, 0.3% of FLOPs)
+        o = o.reshape(B, H, W, c)
         return _conv(self, "proj_out", self.proj_out, o, 1, (0, 0), residual=x)
 
     def forward(self, x: Tensor) -> Tensor:

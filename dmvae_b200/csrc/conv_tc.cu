@@ -314,23 +314,31 @@ struct WgGeom {
     int B, H, W, Cin, Cout, KH, KW, pt, pl;
     int BW, BH, tiles_w, tiles_h;
     int pix_tiles;          // B * tiles_h * tiles_w
-    int co_tiles, ci_tiles, splits, tiles_per_split;
+    int co_tiles, ci_tiles, tap_groups, splits, tiles_per_split;
 };
 
-template <int BN> struct WgCfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr int A_BYTES = 2 * WG_BOX_BYTES;
-    static constexpr int B_BYTES = (BN / 64) * WG_BOX_BYTES;
+// One CTA owns an (MT*128 co) x (TPC taps x BN ci) block of the tap-major gradient and walks a contiguous range of
+// 64-pixel tiles (split-K).  MT = 2 and/or TPC > 1 raise the MACs per operand byte fetched from L2
+// (43.7 -> 65 MAC/B for 512x512, 32 -> 48 for the 128-channel layers), which is what bounds this kernel.
+template <int BN, int MT, int TPC> struct WgCfg {
+    static constexpr int A_BYTES = MT * 2 * WG_BOX_BYTES;
+    static constexpr int B_BYTES_TAP = (BN / 64) * WG_BOX_BYTES;
+    static constexpr int B_BYTES = TPC * B_BYTES_TAP;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-    static constexpr uint32_t TMEM_COLS = BN;
+    static constexpr int ACC_COLS = MT * TPC * BN;
+    static constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+    static constexpr int EPI_WARPS = 4 * MT;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int MT, int TPC>
+__global__ void __launch_bounds__(WgCfg<BN, MT, TPC>::THREADS, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                      float* __restrict__ dwp, WgGeom g) {
-    using C = WgCfg<BN>;
+    using C = WgCfg<BN, MT, TPC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -340,13 +348,14 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // blockIdx.x -> (co tile, ci tile, tap) ; blockIdx.y -> pixel split
+    // blockIdx.x -> (co tile, ci tile, tap group) ; blockIdx.y -> pixel split
     int id = blockIdx.x;
     const int co_t = id % g.co_tiles; id /= g.co_tiles;
     const int ci_t = id % g.ci_tiles; id /= g.ci_tiles;
-    const int tap = id;
-    const int kh = tap / g.KW, kw = tap % g.KW;
-    const int co0 = co_t * BM, ci0 = ci_t * BN;
+    const int tap0 = id * TPC;
+    const int taps = g.KH * g.KW;
+    const int ntap = (taps - tap0 < TPC) ? taps - tap0 : TPC;     // last group may be partial
+    const int co0 = co_t * (BM * MT), ci0 = ci_t * BN;
     const int t_begin = blockIdx.y * g.tiles_per_split;
     const int t_end = (t_begin + g.tiles_per_split < g.pix_tiles) ? t_begin + g.tiles_per_split : g.pix_tiles;
     const int k_iters = t_end - t_begin;
@@ -367,18 +376,23 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            const uint32_t tx = C::A_BYTES + ntap * C::B_BYTES_TAP;
             for (int t = t_begin; t < t_end; ++t) {
                 const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, b = t / (g.tiles_w * g.tiles_h);
                 const int w0 = tw * g.BW, h0 = th * g.BH;
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * C::STAGE_BYTES;
                 uint8_t* sb = sa + C::A_BYTES;
-                mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                mbar_expect_tx(&full[stage], tx);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) tma_load_4d(sa + j * WG_BOX_BYTES, &map_dy, &full[stage], co0 + j * 64, w0, h0, b);
+                for (int j = 0; j < 2 * MT; ++j) tma_load_4d(sa + j * WG_BOX_BYTES, &map_dy, &full[stage], co0 + j * 64, w0, h0, b);
+                for (int tp = 0; tp < ntap; ++tp) {
+                    const int kh = (tap0 + tp) / g.KW, kw = (tap0 + tp) % g.KW;
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j)
-                    tma_load_4d(sb + j * WG_BOX_BYTES, &map_x, &full[stage], ci0 + j * 64, w0 + kw - g.pl, h0 + kh - g.pt, b);
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_4d(sb + tp * C::B_BYTES_TAP + j * WG_BOX_BYTES, &map_x, &full[stage], ci0 + j * 64,
+                                    w0 + kw - g.pl, h0 + kh - g.pt, b);
+                }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -390,12 +404,18 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-                const uint64_t adesc = make_mnmajor_sw128_desc(sa);
-                const uint64_t bdesc = make_mnmajor_sw128_desc(sa + C::A_BYTES);
+                for (int tp = 0; tp < ntap; ++tp) {
+                    const uint64_t bdesc = make_mnmajor_sw128_desc(sa + C::A_BYTES + tp * C::B_BYTES_TAP);
 #pragma unroll
-                for (int kk = 0; kk < WG_PIX / UMMA_K; ++kk) {
-                    // 16 pixels = 16 rows of 128 B = 2048 B along K: +128 in 16-byte units
-                    umma_bf16(tmem_base, adesc + 128 * kk, bdesc + 128 * kk, idesc, (k | kk) != 0);
+                    for (int sub = 0; sub < MT; ++sub) {
+                        const uint64_t adesc = make_mnmajor_sw128_desc(sa + sub * 2 * WG_BOX_BYTES);
+                        const uint32_t d_tmem = tmem_base + (sub * TPC + tp) * BN;
+#pragma unroll
+                        for (int kk = 0; kk < WG_PIX / UMMA_K; ++kk) {
+                            // 16 pixels = 16 rows of 128 B = 2048 B along K: +128 in 16-byte units
+                            umma_bf16(d_tmem, adesc + 128 * kk, bdesc + 128 * kk, idesc, (k | kk) != 0);
+                        }
+                    }
                 }
                 umma_commit(&empty[stage]);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -404,25 +424,28 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
         }
     } else {
         const int lg = warp & 3;
-        const int co = co0 + lg * 32 + lane;
+        const int sub = (warp - 2) >> 2;
+        const int co = co0 + sub * BM + lg * 32 + lane;
         if (k_iters > 0) {
             mbar_wait(tfull, 0);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
+            for (int tp = 0; tp < ntap; ++tp) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (sub * TPC + tp) * BN;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                const int ci = ci0 + c0;
-                if (co < g.Cout && ci < g.Cin) {
-                    float* dst = dwp + ((int64_t)tap * g.Cout + co) * g.Cin + ci;
-                    if (ci + 32 <= g.Cin) {
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    const int ci = ci0 + c0;
+                    if (co < g.Cout && ci < g.Cin) {
+                        float* dst = dwp + ((int64_t)(tap0 + tp) * g.Cout + co) * g.Cin + ci;
+                        if (ci + 32 <= g.Cin) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                    } else {
-                        for (int e = 0; e < 32 && ci + e < g.Cin; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
+                            for (int q = 0; q < 8; ++q)
+                                red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                           __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                        } else {
+                            for (int e = 0; e < 32 && ci + e < g.Cin; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
+                        }
                     }
                 }
             }
@@ -602,9 +625,9 @@ int pick_pixel_tile64(int H, int W, int* BW, int* BH) {
     return 1;
 }
 
-template <int BN>
+template <int BN, int MT, int TPC>
 int launch_wgrad_tc(const void* x, const void* dy, float* dwp, WgGeom g, cudaStream_t st) {
-    using C = WgCfg<BN>;
+    using C = WgCfg<BN, MT, TPC>;
     CUtensorMap mdy, mx;
     const uint32_t box[4] = {64, (uint32_t)g.BW, (uint32_t)g.BH, 1};
     const uint64_t ddims[4] = {(uint64_t)g.Cout, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
@@ -615,19 +638,22 @@ int launch_wgrad_tc(const void* x, const void* dy, float* dwp, WgGeom g, cudaStr
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, MT, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return dmvae_set_error(DMVAE_ECUDA, "conv_tc_wgrad: smem attribute: %s", cudaGetErrorString(e));
         attr_done = true;
     }
+    const int taps = g.KH * g.KW;
+    g.co_tiles = (g.Cout + BM * MT - 1) / (BM * MT);
     g.ci_tiles = (g.Cin + BN - 1) / BN;
-    const int base = g.co_tiles * g.ci_tiles * g.KH * g.KW;
-    int splits = (148 + base - 1) / base;
+    g.tap_groups = (taps + TPC - 1) / TPC;
+    const int base = g.co_tiles * g.ci_tiles * g.tap_groups;
+    int splits = num_sms() / base;                 // fill one wave without spilling into a second
     if (splits > g.pix_tiles) splits = g.pix_tiles;
     if (splits < 1) splits = 1;
     g.tiles_per_split = (g.pix_tiles + splits - 1) / splits;
     g.splits = (g.pix_tiles + g.tiles_per_split - 1) / g.tiles_per_split;
     dim3 grid((unsigned)base, (unsigned)g.splits);
-    conv_tc_wgrad_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(mdy, mx, dwp, g);
+    conv_tc_wgrad_kernel<BN, MT, TPC><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mdy, mx, dwp, g);
     DMVAE_CHECK_LAUNCH("conv_tc_wgrad_kernel");
     return DMVAE_OK;
 }
@@ -654,10 +680,15 @@ DMVAE_API int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_m
     pick_pixel_tile64(H, W, &g.BW, &g.BH);
     g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
     g.pix_tiles = B * g.tiles_w * g.tiles_h;
-    g.co_tiles = (Cout + BM - 1) / BM;
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cin >= 256) return launch_wgrad_tc<256>(x, dy, dw_tap_major, g, st);
-    return launch_wgrad_tc<128>(x, dy, dw_tap_major, g, st);
+    const bool wide_m = Cout >= 256 && g_force_mt != 1;          // two 128-row co tiles per CTA
+    if (Cin >= 256) {
+        return wide_m ? launch_wgrad_tc<256, 2, 1>(x, dy, dw_tap_major, g, st)
+                      : launch_wgrad_tc<256, 1, 1>(x, dy, dw_tap_major, g, st);
+    }
+    if (wide_m) return launch_wgrad_tc<128, 2, 2>(x, dy, dw_tap_major, g, st);
+    if (g_force_mt == 1) return launch_wgrad_tc<128, 1, 1>(x, dy, dw_tap_major, g, st);
+    return launch_wgrad_tc<128, 1, 3>(x, dy, dw_tap_major, g, st);
 }
 
 // test / tuning hook: 0 = heuristic, 1 = 128-pixel tiles, 2 = 256-pixel tiles where the shape allows

@@ -96,6 +96,36 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const uint4* __rest
     }
 }
 
+// any channel count (tiny latent stems): one thread per output element
+__global__ void __launch_bounds__(256) upsample2x_fwd_scalar_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                                    int64_t B, int H, int W, int C) {
+    const int64_t n = B * (2 * H) * (2 * W) * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        int64_t p = i / C;
+        const int ow = (int)(p % (2 * W)); p /= (2 * W);
+        const int oh = (int)(p % (2 * H));
+        const int64_t b = p / (2 * H);
+        y[i] = x[((b * H + (oh >> 1)) * W + (ow >> 1)) * C + c];
+    }
+}
+__global__ void __launch_bounds__(256) upsample2x_bwd_scalar_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                                                                    int64_t B, int H, int W, int C) {
+    const int64_t n = B * H * W * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        int64_t p = i / C;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int64_t b = p / H;
+        float a = 0.f;
+        for (int dh = 0; dh < 2; ++dh)
+            for (int dw = 0; dw < 2; ++dw)
+                a += __bfloat162float(dy[((b * 2 * H + 2 * h + dh) * 2 * W + 2 * w + dw) * C + c]);
+        dx[i] = __float2bfloat16_rn(a);
+    }
+}
+
 static unsigned ew_grid(int64_t n) {
     int64_t g = ceil_div64(n, 256);
     if (g > 148 * 16) g = 148 * 16;
@@ -105,8 +135,14 @@ static unsigned ew_grid(int64_t n) {
 
 DMVAE_API int dmvae_upsample2x_fwd(const void* x, void* y, int64_t B, int H, int W, int C, void* stream) {
     DMVAE_CHECK_ARG(x && y, "upsample2x_fwd: null pointer");
-    DMVAE_CHECK_ARG(C % 8 == 0, "upsample2x_fwd: C must be a multiple of 8 (got %d)", C);
-    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "upsample2x_fwd: buffers must be 16-byte aligned");
+    DMVAE_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0, "upsample2x_fwd: bad shape");
+    if (C % 8 != 0 || ((uintptr_t)x & 15) || ((uintptr_t)y & 15)) {
+        const int64_t ne = B * 4 * H * W * C;
+        if (ne == 0) return DMVAE_OK;
+        upsample2x_fwd_scalar_kernel<<<ew_grid(ne), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C);
+        DMVAE_CHECK_LAUNCH("upsample2x_fwd_scalar_kernel");
+        return DMVAE_OK;
+    }
     const int64_t n = B * 4 * H * W * (C / 8);
     if (n == 0) return DMVAE_OK;
     upsample2x_fwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, B, H, W, C / 8);
@@ -117,8 +153,14 @@ DMVAE_API int dmvae_upsample2x_fwd(const void* x, void* y, int64_t B, int H, int
 // dy: [B][2H][2W][C] -> dx: [B][H][W][C] (sum of the 4 replicas, fp32 accumulate)
 DMVAE_API int dmvae_upsample2x_bwd(const void* dy, void* dx, int64_t B, int H, int W, int C, void* stream) {
     DMVAE_CHECK_ARG(dy && dx, "upsample2x_bwd: null pointer");
-    DMVAE_CHECK_ARG(C % 8 == 0, "upsample2x_bwd: C must be a multiple of 8 (got %d)", C);
-    DMVAE_CHECK_ARG(((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0, "upsample2x_bwd: buffers must be 16-byte aligned");
+    DMVAE_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0, "upsample2x_bwd: bad shape");
+    if (C % 8 != 0 || ((uintptr_t)dy & 15) || ((uintptr_t)dx & 15)) {
+        const int64_t ne = B * H * W * C;
+        if (ne == 0) return DMVAE_OK;
+        upsample2x_bwd_scalar_kernel<<<ew_grid(ne), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)dx, B, H, W, C);
+        DMVAE_CHECK_LAUNCH("upsample2x_bwd_scalar_kernel");
+        return DMVAE_OK;
+    }
     const int64_t n = B * H * W * (C / 8);
     if (n == 0) return DMVAE_OK;
     upsample2x_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (uint4*)dx, B, H, W, C / 8);

@@ -74,6 +74,37 @@ class vgg16(nn.Module):
             outs.append(h)
         return outs
 
+    def _frozen_operands(self, dtype):
+        """Conv weights in `dtype`, channels-last, cached across steps (the net is frozen): saves the per-call
+        fp32->bf16 autocast casts and cuDNN's NCHW->NHWC filter transposes."""
+        key = (dtype, tuple(p._version for p in self.parameters()), next(self.parameters()).device)
+        cache = self.__dict__.get("_wcache")
+        if cache is None or cache[0] != key:
+            ops_ = {}
+            for name, m in self.named_modules():
+                if isinstance(m, nn.Conv2d):
+                    ops_[name] = (m.weight.detach().to(dtype).contiguous(memory_format=torch.channels_last),
+                                  m.bias.detach().to(dtype))
+            cache = (key, ops_)
+            self.__dict__["_wcache"] = cache
+        return cache[1]
+
+    def forward_frozen(self, X, dtype):
+        """Same graph as forward() for frozen weights, X already channels-last in `dtype`."""
+        w = self._frozen_operands(dtype)
+        outs, h = [], X
+        for k in range(1, 6):
+            for name, m in getattr(self, f"slice{k}").named_children():
+                if isinstance(m, nn.Conv2d):
+                    wt, b = w[f"slice{k}.{name}"]
+                    h = nn.functional.conv2d(h, wt, b, padding=1)
+                elif isinstance(m, nn.ReLU):
+                    h = torch.relu(h)
+                else:
+                    h = nn.functional.max_pool2d(h, 2, 2)
+            outs.append(h)
+        return outs
+
 
 class ScalingLayer(nn.Module):
     def __init__(self):
@@ -130,9 +161,17 @@ class LPIPS(nn.Module):
         if faithful is None:
             faithful = torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
         cl = torch.channels_last
-        with torch.no_grad():
-            f0 = self.net(self.scaling_layer(input).contiguous(memory_format=cl))
-        f1 = self.net(self.scaling_layer(target).contiguous(memory_format=cl))
+        frozen = not any(p.requires_grad for p in self.net.parameters())
+        if frozen and input.is_cuda and torch.is_autocast_enabled():
+            dt = torch.get_autocast_dtype("cuda")
+            with torch.autocast("cuda", enabled=False):
+                with torch.no_grad():
+                    f0 = self.net.forward_frozen(self.scaling_layer(input).to(dt).contiguous(memory_format=cl), dt)
+                f1 = self.net.forward_frozen(self.scaling_layer(target).to(dt).contiguous(memory_format=cl), dt)
+        else:
+            with torch.no_grad():
+                f0 = self.net(self.scaling_layer(input).contiguous(memory_format=cl))
+            f1 = self.net(self.scaling_layer(target).contiguous(memory_format=cl))
         val = None
         for k in range(5):
             w = getattr(self, f"lin{k}").weight

@@ -268,6 +268,42 @@ class ToNchwFn(torch.autograd.Function):
         return dx, None
 
 
+class SingleHeadAttentionFn(torch.autograd.Function):
+    """softmax(q k^T / sqrt(C)) v for one head of width C (models/flux_ae.py:43-47: SDPA with a single 512-wide head).
+
+    Library GEMMs (cuBLAS bmm) with fp32 logits, fp32 softmax and bf16 probabilities -- the same rounding points as
+    the fused SDPA kernels the reference dispatches to.  Written as explicit GEMMs because at head_dim 512 the
+    stock SDPA backward falls back to a memory-efficient kernel that takes ~3 ms per step here (N4 in SURVEY 8(f)
+    replaces this with a tcgen05 flash kernel)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v):
+        # q, k, v: (B, N, C) bf16 contiguous
+        scale = q.shape[-1] ** -0.5
+        s = torch.bmm(q, k.transpose(1, 2), out_dtype=torch.float32)
+        p = torch.softmax(s * scale, dim=-1).to(q.dtype)
+        o = torch.bmm(p, v)
+        ctx.save_for_backward(q, k, v, p)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, p = ctx.saved_tensors
+        do = do.contiguous()
+        dv = torch.bmm(p.transpose(1, 2), do)
+        dp = torch.bmm(do, v.transpose(1, 2), out_dtype=torch.float32)
+        pf = p.float()
+        ds = (pf * (dp - (dp * pf).sum(-1, keepdim=True)) * ctx.scale).to(q.dtype)
+        dq = torch.bmm(ds, k)
+        dk = torch.bmm(ds.transpose(1, 2), q)
+        return dq, dk, dv
+
+
+def single_head_attention(q, k, v):
+    return SingleHeadAttentionFn.apply(q, k, v)
+
+
 def conv2d(x, weight, bias, pack: WeightPack, stride: int = 1, pad_tl=(1, 1), residual=None, pad_br=None):
     return ConvFn.apply(x, weight, bias, residual, pack, stride, pad_tl, pad_br)
 

@@ -246,11 +246,13 @@ def _conv_case(B, cin, cout, H, W, k, stride, pad_tl, residual, force_direct, se
     assert rel_err(nchw(dx), dx_ref) < 4e-3, "dgrad"
     assert rel_err(dw, wr.grad) < 1e-3, "wgrad"
     assert rel_err(db, dy.sum((0, 2, 3))) < 1e-3, "bias grad"
-    # element-wise bound as well: one bf16 ulp (2^-8) of the larger of output / conv term (the residual add can
-    # cancel), plus fp32 accumulation-order noise scaled by the typical magnitude
+    # element-wise bound as well.  One bf16 ulp is between 2^-8 and 2^-7 relative; a rounding flip costs one ulp of
+    # the conv term and, with the residual add, one more of the sum: <= 2 * 2^-7 of the larger of the two (the add can
+    # cancel), plus fp32 accumulation-order noise scaled by the typical magnitude.
     yy, rr = nchw(y), y_full
     mag = torch.maximum(rr.abs(), y_ref.detach().abs())
-    assert ((yy - rr).abs() <= 2 ** -7 * mag + 2 ** -8 * rr.abs().mean()).all()
+    nulp = 2 if residual else 1
+    assert ((yy - rr).abs() <= nulp * 2 ** -7 * mag + 2 ** -8 * rr.abs().mean()).all()
 
 
 @pytest.mark.parametrize("case", [

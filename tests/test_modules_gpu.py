@@ -128,7 +128,8 @@ def test_retain_graph_partial_grads_and_inference_mode():
     g1 = torch.autograd.grad(l_a, last, retain_graph=True)[0]
     g2 = torch.autograd.grad(l_b, last, retain_graph=True)[0]
     (l_a + l_b).backward()
-    assert rel(last.grad, g1 + g2) < 1e-5
+    # the upstream gradient crosses the module boundary in bf16: bf16(ga) + bf16(gb) vs bf16(ga + gb)
+    assert rel(last.grad, g1 + g2) < 5e-3
     with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
         y2 = dec(z)
     assert torch.equal(y2.float(), y.detach())          # same kernels, deterministic forward
