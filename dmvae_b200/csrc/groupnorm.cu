@@ -39,12 +39,10 @@ static void gn_grid(int64_t B, int64_t HW, int rows, dim3* grid, int64_t* ppb) {
 // stats[b][g] = {sum, sumsq} (fp64, caller zero-initialised)
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ stats,
                                                               int64_t HW, int C, int vc, int rows, int64_t ppb) {
-    __shared__ float s_acc[GN_GROUPS * 2];
+    __shared__ float s_part[2 * GN_THREADS * 8];      // per-thread {sum[8], sumsq[8]}
     const int b = blockIdx.y;
     const int col = threadIdx.x % vc, row = threadIdx.x / vc;
     const int cpg = C / GN_GROUPS;
-    if (threadIdx.x < GN_GROUPS * 2) s_acc[threadIdx.x] = 0.f;
-    __syncthreads();
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
     float s[8], ss[8];
@@ -66,24 +64,19 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __rest
             for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] += f[k] * f[k]; }
         }
     }
-    if (cpg >= 8) {
-        float a = 0.f, q = 0.f;
+    // fixed-order fan-in (no floating-point atomics inside the CTA): the forward pass is run-to-run reproducible up to
+    // the order of the per-CTA fp64 atomics below, which is far under fp32 resolution.
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { a += s[k]; q += ss[k]; }
-        const int g = (col * 8) / cpg;
-        atomicAdd(&s_acc[2 * g], a);
-        atomicAdd(&s_acc[2 * g + 1], q);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int g = (col * 8 + k) / cpg;
-            atomicAdd(&s_acc[2 * g], s[k]);
-            atomicAdd(&s_acc[2 * g + 1], ss[k]);
-        }
-    }
+    for (int k = 0; k < 8; ++k) { s_part[threadIdx.x * 8 + k] = s[k]; s_part[(GN_THREADS + threadIdx.x) * 8 + k] = ss[k]; }
     __syncthreads();
-    if (threadIdx.x < GN_GROUPS * 2)
-        atomicAdd(&stats[(int64_t)b * GN_GROUPS * 2 + threadIdx.x], (double)s_acc[threadIdx.x]);
+    if (threadIdx.x < GN_GROUPS * 2) {
+        const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const float* part = s_part + which * GN_THREADS * 8;
+        float acc = 0.f;
+        for (int r = 0; r < rows; ++r)
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += part[(r * vc + (c >> 3)) * 8 + (c & 7)];
+        atomicAdd(&stats[(int64_t)b * GN_GROUPS * 2 + threadIdx.x], (double)acc);
+    }
 }
 
 __device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ stats, int b, int g, double n, float eps,

@@ -14,6 +14,7 @@ import warnings
 import torch
 from torch import nn
 
+from . import ops
 from .losses import lpips_tap_distance
 
 _VGG_PLAN = [  # torchvision vgg16.features indices: (idx, kind, cin, cout)
@@ -89,6 +90,28 @@ class vgg16(nn.Module):
             self.__dict__["_wcache"] = cache
         return cache[1]
 
+    def forward_b200(self, X):
+        """Frozen-weight VGG16 pass on the library's own conv tiles: channels-last bf16 activations,
+        tcgen05 implicit-GEMM convs (thin-input kernel for the 3->64 stem), same bf16/fp32 rounding points as the
+        autocast'ed cuDNN path.  ReLU / max-pool stay ATen elementwise ops.  X: (B, 3, H, W) fp32 or bf16."""
+        packs = self.__dict__.setdefault("_packs", {})
+        h = ops.to_channels_last(X)                                   # (B, H, W, 3) bf16
+        outs = []
+        for k in range(1, 6):
+            for name, m in getattr(self, f"slice{k}").named_children():
+                if isinstance(m, nn.Conv2d):
+                    key = f"slice{k}.{name}"
+                    pack = packs.get(key)
+                    if pack is None:
+                        pack = packs[key] = ops.WeightPack()
+                    h = ops.conv2d(h, m.weight, m.bias, pack)
+                elif isinstance(m, nn.ReLU):
+                    h = torch.relu(h)
+                else:
+                    h = nn.functional.max_pool2d(h.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+            outs.append(h.permute(0, 3, 1, 2))                        # NCHW-logical view of the channels-last buffer
+        return outs
+
     def forward_frozen(self, X, dtype):
         """Same graph as forward() for frozen weights, X already channels-last in `dtype`."""
         w = self._frozen_operands(dtype)
@@ -131,10 +154,13 @@ class NetLinLayer(nn.Module):
 
 
 class LPIPS(nn.Module):
-    def __init__(self, ckpt_path=None, use_dropout=True, pretrained_vgg=True, faithful=None):
+    def __init__(self, ckpt_path=None, use_dropout=True, pretrained_vgg=True, faithful=None, vgg_backend="b200"):
         """faithful: reproduce the bf16 roundings autocast puts around the 1x1 lin conv and the bf16 tail
-        (None = do so exactly when autocast(bf16) is active, as the reference run would)."""
+        (None = do so exactly when autocast(bf16) is active, as the reference run would).
+        vgg_backend: "b200" runs the frozen VGG16 convs on this library's tcgen05 tiles under autocast(bf16);
+        "cudnn" keeps them on cuDNN (the reference's path)."""
         super().__init__()
+        self.vgg_backend = vgg_backend
         self.scaling_layer = ScalingLayer()
         self.chns = [64, 128, 256, 512, 512]
         self.net = vgg16(pretrained=pretrained_vgg, requires_grad=False)
@@ -162,7 +188,13 @@ class LPIPS(nn.Module):
             faithful = torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
         cl = torch.channels_last
         frozen = not any(p.requires_grad for p in self.net.parameters())
-        if frozen and input.is_cuda and torch.is_autocast_enabled():
+        if frozen and input.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16 \
+                and self.vgg_backend == "b200":
+            with torch.autocast("cuda", enabled=False):
+                with torch.no_grad():
+                    f0 = self.net.forward_b200(self.scaling_layer(input.float()))
+                f1 = self.net.forward_b200(self.scaling_layer(target.float()))
+        elif frozen and input.is_cuda and torch.is_autocast_enabled():
             dt = torch.get_autocast_dtype("cuda")
             with torch.autocast("cuda", enabled=False):
                 with torch.no_grad():

@@ -132,10 +132,11 @@ def test_retain_graph_partial_grads_and_inference_mode():
     assert rel(last.grad, g1 + g2) < 5e-3
     with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
         y2 = dec(z)
-    assert torch.equal(y2.float(), y.detach())          # same kernels, deterministic forward
+    # same kernels; the only order-dependent step is the fp64 fan-in of the GroupNorm statistics across CTAs
+    assert rel(y2.float(), y.detach()) < 1e-3
     ema = copy.deepcopy(dec)                            # EMA copy (train_tokenizer.py:397)
     with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
-        assert torch.equal(ema(z), y2)
+        assert rel(ema(z).float(), y2.float()) < 1e-3
     with torch.no_grad():                               # weight update must invalidate the packed bf16 operands
         dec.conv_out.weight.mul_(2.0); dec.conv_out.bias.mul_(2.0)
     with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
@@ -161,11 +162,18 @@ def test_lpips_module_vs_oracle_fp32():
     val.backward()
     assert abs(val.item() - ref.item()) < 1e-3 * abs(ref.item())
     assert rel(bc.grad, br.grad) < 1e-2
-    # autocast run: within the reference's own bf16 noise (outputs are bf16: 2^-8)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        v16 = lp(a.to(DEV), b.to(DEV))
-    ref16 = O.lpips_forward(sd, a, b, bf16=True)
-    assert abs(v16.float().item() - ref16.item()) < 3e-2 * abs(ref16.item())
+    # autocast runs (VGG on our tcgen05 tiles, and on cuDNN): within the reference's own bf16 noise (2^-8 per rounding)
+    br16 = b.clone().requires_grad_(True)
+    ref16 = O.lpips_forward(sd, a, br16, bf16=True)
+    ref16.backward()
+    for backend in ("b200", "cudnn"):
+        lp.vgg_backend = backend
+        bc16 = b.to(DEV).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            v16 = lp(a.to(DEV), bc16)
+        v16.float().backward()
+        assert abs(v16.float().item() - ref16.item()) < 3e-2 * abs(ref16.item()), backend
+        assert rel(bc16.grad, br16.grad) < 5e-2, backend
 
 
 def test_tokenizer_trainer_steps_and_loss_goes_down():
