@@ -191,6 +191,91 @@ __global__ void __launch_bounds__(256) dmd_loss_kernel(
     }
 }
 
+// ---- bf16 fast path: the same op-by-op bf16 arithmetic on packed pairs -------------------------------------------
+// mul/add/sub.rn.bf16x2 round the exact result once.  That equals the reference's "compute in fp32, round to bf16"
+// for these ops: a product of two bf16 values is exact in fp32, and a sum of two bf16 values is either exact in fp32
+// or dominated by one operand beyond bf16 resolution.  ~3x fewer instructions than the scalar path, which is what
+// the kernel was bound by (it issues ~90 instructions per element otherwise).
+typedef __nv_bfloat162 bf2;
+__device__ __forceinline__ bf2 u2b(uint32_t u) { return *reinterpret_cast<bf2*>(&u); }
+__device__ __forceinline__ uint32_t b2u(bf2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+template <typename TD>
+__global__ void __launch_bounds__(256) dmd_loss_bf16x2_kernel(
+    const bf16* __restrict__ z, const bf16* __restrict__ xt, const bf16* __restrict__ t,
+    const bf16* __restrict__ vTc, const bf16* __restrict__ vTu, const bf16* __restrict__ vSc, const bf16* __restrict__ vSu,
+    TD* __restrict__ dz, double* __restrict__ acc, int64_t P, float cfg_m1, int use_cfg, int normalize, float dz_scale) {
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    __shared__ float red[64];
+    __shared__ float s_w;
+    uint4* s_z = reinterpret_cast<uint4*>(dyn_raw);
+    uint4* s_d = s_z + P / 8;
+    const int64_t b = blockIdx.x;
+    const int64_t base = b * P;
+    const float tb = __bfloat162float(t[b]);
+    const bf16 omt1 = __float2bfloat16_rn(__fsub_rn(1.f, tb));
+    const bf2 omt = __halves2bfloat162(omt1, omt1);
+    const bf16 c1 = __float2bfloat16_rn(cfg_m1);
+    const bf2 cm = __halves2bfloat162(c1, c1);
+    const int nv = (int)(P / 8);
+
+    float v[1] = {0.f};
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+        const int64_t e0 = base + (int64_t)j * 8;
+        const uint4 Z = ld_stream16(z + e0), X = ld_stream16(xt + e0), A = ld_stream16(vTc + e0), S = ld_stream16(vSc + e0);
+        uint4 AU = make_uint4(0, 0, 0, 0), SU = AU;
+        if (use_cfg) { AU = ld_stream16(vTu + e0); SU = ld_stream16(vSu + e0); }
+        const uint32_t zq[4] = {Z.x, Z.y, Z.z, Z.w}, xq[4] = {X.x, X.y, X.z, X.w}, aq[4] = {A.x, A.y, A.z, A.w},
+                       sq[4] = {S.x, S.y, S.z, S.w}, auq[4] = {AU.x, AU.y, AU.z, AU.w}, suq[4] = {SU.x, SU.y, SU.z, SU.w};
+        uint32_t dq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            bf2 vt = u2b(aq[q]), vs = u2b(sq[q]);
+            if (use_cfg) {                                                   // v + (s-1)*(v - v_uncond)
+                vt = __hadd2(vt, __hmul2(cm, __hsub2(vt, u2b(auq[q]))));
+                vs = __hadd2(vs, __hmul2(cm, __hsub2(vs, u2b(suq[q]))));
+            }
+            const bf2 xx = u2b(xq[q]), zz = u2b(zq[q]);
+            const bf2 pr = __hsub2(zz, __hadd2(xx, __hmul2(vt, omt)));       // z - (xt + v_T (1-t))
+            const bf2 ps = __hsub2(zz, __hadd2(xx, __hmul2(vs, omt)));
+            dq[q] = b2u(__hsub2(pr, ps));
+            const bf2 ap = __habs2(pr);
+            v[0] += __low2float(ap) + __high2float(ap);
+        }
+        s_z[j] = Z;
+        s_d[j] = make_uint4(dq[0], dq[1], dq[2], dq[3]);
+    }
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) s_w = bf16_round(v[0] / (float)P);
+    __syncthreads();
+    const float w = s_w;
+
+    float a[2] = {0.f, 0.f};
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+        const uint4 Z = s_z[j], D = s_d[j];
+        const uint32_t zq[4] = {Z.x, Z.y, Z.z, Z.w}, dq[4] = {D.x, D.y, D.z, D.w};
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float g0 = __low2float(u2b(dq[q])), g1 = __high2float(u2b(dq[q]));
+            if (normalize) { g0 = bf16_round(__fdiv_rn(g0, w)); g1 = bf16_round(__fdiv_rn(g1, w)); }
+            g0 = nan_to_num<bf16>(g0); g1 = nan_to_num<bf16>(g1);
+            const bf2 zz = u2b(zq[q]);
+            const bf2 tg = __hsub2(zz, __floats2bfloat162_rn(g0, g1));      // (latents - grad), bf16
+            const float e0 = __fsub_rn(__low2float(zz), __low2float(tg)), e1 = __fsub_rn(__high2float(zz), __high2float(tg));
+            a[0] += e0 * e0 + e1 * e1;
+            a[1] += g0 * g0 + g1 * g1;
+            o[2 * q] = e0 * dz_scale; o[2 * q + 1] = e1 * dz_scale;
+        }
+        store_n<TD, 8>(dz + base + (int64_t)j * 8, o);
+    }
+    block_sum<2>(a, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&acc[0], (double)a[0]);
+        atomicAdd(&acc[1], (double)sqrtf(a[1]));
+    }
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <typename T, typename TD, bool VEC>
@@ -221,6 +306,19 @@ static int launch_dmd(const void* z, const void* xt, const void* t, const void* 
     const float cfg_m1 = cfg_scale - 1.f;
     const bool vec = (P % Vec<T>::N == 0) && aligned16(z) && aligned16(xt) && aligned16(vTc) && aligned16(vSc) &&
                      aligned16(dz) && (!use_cfg || (aligned16(vTu) && aligned16(vSu)));
+    if constexpr (sizeof(T) == 2) {
+        // packed bf16x2 path: needs the CFG multiplier to be exactly representable in bf16 (4.0 for the default scale 5)
+        const float c_r = __bfloat162float(__float2bfloat16_rn(cfg_m1));
+        const size_t cache_bytes = (size_t)P * 4;
+        if (vec && (!use_cfg || c_r == cfg_m1) && cache_bytes <= 96 * 1024) {
+            auto k = dmd_loss_bf16x2_kernel<TD>;
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            k<<<(unsigned)B, 256, cache_bytes, st>>>((const bf16*)z, (const bf16*)xt, (const bf16*)t, (const bf16*)vTc, (const bf16*)vTu,
+                                                     (const bf16*)vSc, (const bf16*)vSu, (TD*)dz, acc, P, cfg_m1, use_cfg, normalize, dz_scale);
+            DMVAE_CHECK_LAUNCH("dmd_loss_bf16x2_kernel");
+            return DMVAE_OK;
+        }
+    }
     return vec ? launch_dmd_v<T, TD, true>(z, xt, t, vTc, vTu, vSc, vSu, dz, acc, B, P, cfg_m1, use_cfg, normalize, dz_scale, st)
                : launch_dmd_v<T, TD, false>(z, xt, t, vTc, vTu, vSc, vSu, dz, acc, B, P, cfg_m1, use_cfg, normalize, dz_scale, st);
 }

@@ -36,7 +36,7 @@ def nchw(y):  # (B,H,W,C) cuda -> (B,C,H,W) fp32 cpu
 
 # ------------------------------------------------------------------------------------------------ A3
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("cfg,normalize", [(5.0, True), (1.0, True), (1.0, False)])
+@pytest.mark.parametrize("cfg,normalize", [(5.0, True), (3.7, True), (1.0, True), (1.0, False)])
 @pytest.mark.parametrize("shape", [(4, 32, 16, 16), (3, 2, 1, 1), (5, 7, 3, 3)])
 def test_dmd_loss(dtype, cfg, normalize, shape):
     _, L = _ops()
