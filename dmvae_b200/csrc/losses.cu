@@ -662,6 +662,60 @@ __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const T* __restrict
     }
 }
 
+// 16-byte vector variants (half % Vec<T>::N == 0, aligned): one thread handles Vec<T>::N consecutive latents of a row
+template <typename T>
+__global__ void __launch_bounds__(256) reparam_kl_fwd_vec_kernel(const T* __restrict__ h, const T* __restrict__ eps,
+                                                                 T* __restrict__ z, double* __restrict__ acc,
+                                                                 int64_t rows, int64_t half) {
+    constexpr int VN = Vec<T>::N;
+    __shared__ float red[32];
+    const int64_t hv = half / VN, n = rows * hv;
+    float a[1] = {0.f};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / hv, j = (i - r * hv) * VN;
+        float mu[VN], lv[VN], e[VN], o[VN];
+        Vec<T>::load(h + r * 2 * half + j, mu);
+        Vec<T>::load(h + r * 2 * half + half + j, lv);
+        Vec<T>::load(eps + r * half + j, e);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) {
+            const float sd = __expf(0.5f * lv[k]);
+            o[k] = fmaf(sd, e[k], mu[k]);
+            a[0] += 0.5f * (fmaf(mu[k], mu[k], sd * sd) - 1.f - lv[k]);
+        }
+        Vec<T>::store(z + r * half + j, o);
+    }
+    block_sum<1>(a, red);
+    if (threadIdx.x == 0) atomicAdd(&acc[0], (double)a[0]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) reparam_kl_bwd_vec_kernel(const T* __restrict__ h, const T* __restrict__ eps,
+                                                                 const T* __restrict__ dz, T* __restrict__ dh,
+                                                                 const float* __restrict__ g_kl, float kl_scale,
+                                                                 int64_t rows, int64_t half) {
+    constexpr int VN = Vec<T>::N;
+    const int64_t hv = half / VN, n = rows * hv;
+    const float g = kl_scale * (g_kl ? *g_kl : 1.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / hv, j = (i - r * hv) * VN;
+        float mu[VN], lv[VN], e[VN], d[VN], o1[VN], o2[VN];
+        Vec<T>::load(h + r * 2 * half + j, mu);
+        Vec<T>::load(h + r * 2 * half + half + j, lv);
+        Vec<T>::load(eps + r * half + j, e);
+        if (dz) Vec<T>::load(dz + r * half + j, d);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) {
+            const float dk = dz ? d[k] : 0.f;
+            const float sd = __expf(0.5f * lv[k]);
+            o1[k] = fmaf(g, mu[k], dk);
+            o2[k] = dk * e[k] * 0.5f * sd + g * 0.5f * (sd * sd - 1.f);
+        }
+        Vec<T>::store(dh + r * 2 * half + j, o1);
+        Vec<T>::store(dh + r * 2 * half + half + j, o2);
+    }
+}
+
 DMVAE_API int dmvae_reparam_kl_fwd(const void* h, const void* eps, void* z, double* acc, int64_t rows,
                                    int64_t half, int dtype, void* stream) {
     DMVAE_CHECK_ARG(h && eps && z && acc, "reparam_kl_fwd: null pointer");
@@ -670,11 +724,14 @@ DMVAE_API int dmvae_reparam_kl_fwd(const void* h, const void* eps, void* z, doub
     if (n == 0) return DMVAE_OK;
     const unsigned grid = stream_grid(n / 2);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == DMVAE_F32)
-        reparam_kl_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)h, (const float*)eps, (float*)z, acc, rows, half);
-    else if (dtype == DMVAE_BF16)
-        reparam_kl_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)h, (const bf16*)eps, (bf16*)z, acc, rows, half);
-    else
+    const bool al = aligned16(h) && aligned16(eps) && aligned16(z);
+    if (dtype == DMVAE_F32) {
+        if (al && half % 4 == 0) reparam_kl_fwd_vec_kernel<float><<<stream_grid(n / 4), 256, 0, st>>>((const float*)h, (const float*)eps, (float*)z, acc, rows, half);
+        else reparam_kl_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)h, (const float*)eps, (float*)z, acc, rows, half);
+    } else if (dtype == DMVAE_BF16) {
+        if (al && half % 8 == 0) reparam_kl_fwd_vec_kernel<bf16><<<stream_grid(n / 8), 256, 0, st>>>((const bf16*)h, (const bf16*)eps, (bf16*)z, acc, rows, half);
+        else reparam_kl_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)h, (const bf16*)eps, (bf16*)z, acc, rows, half);
+    } else
         return dmvae_set_error(DMVAE_EINVAL, "reparam_kl_fwd: bad dtype %d", dtype);
     DMVAE_CHECK_LAUNCH("reparam_kl_fwd_kernel");
     return DMVAE_OK;
@@ -688,11 +745,14 @@ DMVAE_API int dmvae_reparam_kl_bwd(const void* h, const void* eps, const void* d
     if (n == 0) return DMVAE_OK;
     const unsigned grid = stream_grid(n / 2);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == DMVAE_F32)
-        reparam_kl_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)h, (const float*)eps, (const float*)dz, (float*)dh, g_kl, kl_scale, rows, half);
-    else if (dtype == DMVAE_BF16)
-        reparam_kl_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)h, (const bf16*)eps, (const bf16*)dz, (bf16*)dh, g_kl, kl_scale, rows, half);
-    else
+    const bool al = aligned16(h) && aligned16(eps) && aligned16(dh) && aligned16(dz);
+    if (dtype == DMVAE_F32) {
+        if (al && half % 4 == 0) reparam_kl_bwd_vec_kernel<float><<<stream_grid(n / 4), 256, 0, st>>>((const float*)h, (const float*)eps, (const float*)dz, (float*)dh, g_kl, kl_scale, rows, half);
+        else reparam_kl_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)h, (const float*)eps, (const float*)dz, (float*)dh, g_kl, kl_scale, rows, half);
+    } else if (dtype == DMVAE_BF16) {
+        if (al && half % 8 == 0) reparam_kl_bwd_vec_kernel<bf16><<<stream_grid(n / 8), 256, 0, st>>>((const bf16*)h, (const bf16*)eps, (const bf16*)dz, (bf16*)dh, g_kl, kl_scale, rows, half);
+        else reparam_kl_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)h, (const bf16*)eps, (const bf16*)dz, (bf16*)dh, g_kl, kl_scale, rows, half);
+    } else
         return dmvae_set_error(DMVAE_EINVAL, "reparam_kl_bwd: bad dtype %d", dtype);
     DMVAE_CHECK_LAUNCH("reparam_kl_bwd_kernel");
     return DMVAE_OK;
