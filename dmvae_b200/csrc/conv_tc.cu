@@ -284,6 +284,215 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------- CTA-pair variant (cta_group::2)
+// Two CTAs of a cluster (one TPC) cooperate on a 256-pixel x BN tile: each loads its own 128-pixel A tile and HALF of
+// the weight tile; the leader issues tcgen05.mma.cta_group::2 (UMMA M = 256), which reads A from each CTA's own shared
+// memory and the two B halves from both.  Per SM this halves the weight bytes pulled from L2 and read from shared
+// memory (64 B/cycle of tensor-core reads instead of 96), which is what bounds the single-CTA tile.
+//   * TMA loads in both CTAs complete on the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2).
+//   * tcgen05.commit ... multicast::cluster releases the smem slot / publishes the accumulator in BOTH CTAs.
+//   * each CTA's epilogue drains its own 128 TMEM lanes; the peer arrives remotely on the leader's tmem-empty barrier.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN> struct Cfg2 {
+    static constexpr int A_BYTES = BM * BK * 2;                 // this CTA's 128 pixels
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;           // this CTA's half of the weight tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;               // two accumulator buffers of BN columns
+    static constexpr int THREADS = 192;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out, TcGeom g) {
+    using C = Cfg2<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                       // [STAGES]  (the leader's copy is the live one)
+    uint64_t* empty = bars + C::STAGES;          // [STAGES]
+    uint64_t* tfull = bars + 2 * C::STAGES;      // [2]
+    uint64_t* tempty = bars + 2 * C::STAGES + 2; // [2]       (leader's copy is the live one)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int pair_tiles = (g.m_tiles >> 1) * g.n_tiles;
+    const int k_iters = g.KH * g.KW * g.k_chunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer (both CTAs) ==============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+                const int mt = 2 * (pt / g.n_tiles) + (int)rank, nt = pt % g.n_tiles;
+                const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
+                const int w0 = tw * g.BW - g.pl, h0 = th * g.BH - g.pt, n0 = nt * BN + (int)rank * (BN / 2);
+                for (int tap = 0; tap < g.KH * g.KW; ++tap) {
+                    const int kh = tap / g.KW, kw = tap % g.KW;
+                    for (int kc = 0; kc < g.k_chunks; ++kc) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                        uint8_t* sb = sa + C::A_BYTES;
+                        if (leader) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);      // bytes of both CTAs
+                        const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+                        tma_load_4d_2sm(sa, &map_a, lbar, kc * BK, w0 + kw, h0 + kh, b);
+                        tma_load_3d_2sm(sb, &map_b, lbar, kc * BK, n0, tap);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer (leader only) ==============================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_m256(BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);      // both CTAs' epilogues drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int k = 0; k < k_iters; ++k) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint64_t adesc = make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(sa + C::A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                        umma_bf16_2sm(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+                    umma_commit_2sm(&empty[stage]);                 // frees the slot in both CTAs
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tfull[buf]);                       // accumulator ready in both CTAs
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5, both CTAs) ==============================
+        const int lg = warp & 3;
+        const int r = lg * 32 + lane;
+        const int dh = r / g.BW, dw = r % g.BW;
+        int it = 0;
+        for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++it) {
+            const int buf = it & 1;
+            const int mt = 2 * (pt / g.n_tiles) + (int)rank, nt = pt % g.n_tiles;
+            const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
+            const int64_t pix = ((int64_t)b * g.H + th * g.BH + dh) * g.W + tw * g.BW + dw;
+            const int n0 = nt * BN;
+            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                const int n = n0 + c0;
+                if (n >= g.Cout) continue;
+                bf16* op = out + pix * g.Cout + n;
+                const bf16* rp = res ? res + pix * g.Cout + n : nullptr;
+                if (n + 32 <= g.Cout && (g.Cout & 7) == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
+                        if (rp) {
+                            float fr[8];
+                            unpack_bf16x8(*reinterpret_cast<const uint4*>(rp + q * 8), fr);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];
+                        }
+                        *reinterpret_cast<uint4*>(op + q * 8) = pack_bf16x8(f);
+                    }
+                } else {
+                    for (int e = 0; e < 32 && n + e < g.Cout; ++e) {
+                        float f = __uint_as_float(v[e]) + (bias ? __ldg(bias + n + e) : 0.f);
+                        if (rp) f = bf16_round(f) + __bfloat162float(rp[e]);
+                        op[e] = __float2bfloat16_rn(f);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------- weight gradient
 // dWp[tap][co][ci] += sum_pixels dY[p][co] * X[p (+) tap][ci]          M = Cout, N = Cin, K = pixels (split)
 //
@@ -567,8 +776,34 @@ int launch_conv_tc(const void* x, const void* w, const float* bias, const void* 
     return DMVAE_OK;
 }
 
-// 0 = let the heuristic decide, 1 / 2 = force the number of 128-pixel sub-tiles per CTA (tests, tuning)
+template <int BN>
+int launch_conv_tc2(const void* x, const void* w, const float* bias, const void* res, void* y, TcGeom g, cudaStream_t st) {
+    using C = Cfg2<BN>;
+    CUtensorMap ma, mb;
+    const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint32_t abox[4] = {BK, (uint32_t)g.BW, (uint32_t)g.BH, 1};
+    int rc = get_tensor_map(x, 4, adims, abox, &ma);
+    if (rc) return rc;
+    const uint64_t bdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, (uint64_t)(g.KH * g.KW)};
+    const uint32_t bbox[3] = {BK, BN / 2, 1};
+    rc = get_tensor_map(w, 3, bdims, bbox, &mb);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return dmvae_set_error(DMVAE_ECUDA, "conv_tc2: smem attribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int pair_tiles = (g.m_tiles / 2) * g.n_tiles;
+    const int clusters = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
+    conv_tc2_kernel<BN><<<2 * clusters, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, g);
+    DMVAE_CHECK_LAUNCH("conv_tc2_kernel");
+    return DMVAE_OK;
+}
+
+// 0 = let the heuristic decide, 1 / 2 = force the number of 128-pixel sub-tiles per CTA, 3 = force CTA pairs
 int g_force_mt = 0;
+int g_pair_default = 0;      // flipped to 1 once the pair kernel is validated on hardware (dmvae_conv_tc_set_tile_mode(4))
 
 }  // namespace
 
@@ -605,6 +840,18 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     }
     if (g_force_mt == 1) mt = 1;
     if (g_force_mt == 2 && bn >= 128 && pick_pixel_tile_n(H, W, 2 * BM, &bw2, &bh2)) mt = 2;
+    // CTA pairs: 128-pixel tiles per CTA, an even number of them, full N tiles
+    if (bn >= 128 && Cout % bn == 0 && (g_force_mt == 3 || (g_force_mt == 0 && g_pair_default))) {
+        TcGeom gp = g;
+        if (pick_pixel_tile_n(H, W, BM, &gp.BW, &gp.BH)) {
+            gp.tiles_w = W / gp.BW; gp.tiles_h = H / gp.BH;
+            gp.m_tiles = B * gp.tiles_w * gp.tiles_h;
+            if (gp.m_tiles % 2 == 0 && (g_force_mt == 3 || (gp.m_tiles / 2) * gp.n_tiles >= (num_sms() * 3) / 8)) {
+                return bn == 256 ? launch_conv_tc2<256>(x, w_packed, bias, residual, y, gp, st)
+                                 : launch_conv_tc2<128>(x, w_packed, bias, residual, y, gp, st);
+            }
+        }
+    }
     pick_pixel_tile_n(H, W, mt * BM, &g.BW, &g.BH);
     g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
     g.m_tiles = B * g.tiles_w * g.tiles_h;
@@ -693,6 +940,8 @@ DMVAE_API int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_m
 
 // test / tuning hook: 0 = heuristic, 1 = 128-pixel tiles, 2 = 256-pixel tiles where the shape allows
 DMVAE_API int dmvae_conv_tc_set_tile_mode(int mode) {
-    g_force_mt = (mode == 1 || mode == 2) ? mode : 0;
+    if (mode == 4) { g_pair_default = 1; g_force_mt = 0; return DMVAE_OK; }      // heuristic, CTA pairs preferred
+    if (mode == 5) { g_pair_default = 0; g_force_mt = 0; return DMVAE_OK; }      // heuristic, single-CTA tiles only
+    g_force_mt = (mode >= 1 && mode <= 3) ? mode : 0;
     return DMVAE_OK;
 }

@@ -90,10 +90,10 @@ def main():
             wf, wd = ops.WeightPack().get(w)
             flops = 2.0 * B * hw * hw * cin * cout * k * k
             res = {}
-            for mode in (1, 2):
+            for mode in (1, 2, 3):
                 _lib.query("dmvae_conv_tc_set_tile_mode", mode)
                 us = timeit(lambda i: ops.conv_forward_raw(x, wf, bias, None, k, k, 1, ((k - 1) // 2, (k - 1) // 2)), a.iters, 1)
-                res[f"fwd_mt{mode}_tflops"] = round(flops / us / 1e6, 1)
+                res[{1: "fwd_mt1", 2: "fwd_mt2", 3: "fwd_pair"}[mode] + "_tflops"] = round(flops / us / 1e6, 1)
             _lib.query("dmvae_conv_tc_set_tile_mode", 0)
             us = timeit(lambda i: ops.conv_wgrad_raw(x, dy, k, k, 1, ((k - 1) // 2, (k - 1) // 2)), a.iters, 1)
             res["wgrad_tflops"] = round(flops / us / 1e6, 1)

@@ -284,7 +284,7 @@ def test_conv_tcgen05(case):
     _conv_case(*case, force_direct=False)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("case", [
     (2, 128, 128, 16, 16, 3, 1, (1, 1), True),    # BN=128: one 256-pixel tile per image
     (1, 512, 512, 32, 32, 3, 1, (1, 1), True),    # BN=256, single TMEM accumulator set when MT=2
@@ -292,7 +292,7 @@ def test_conv_tcgen05(case):
     (2, 128, 128, 2, 256, 3, 1, (1, 1), False),   # W=256: a 256-pixel tile is one image row
 ])
 def test_conv_tcgen05_tile_modes(case, mode):
-    """Both CTA tile shapes (128 or 256 pixels per CTA) must give the same answers."""
+    """All CTA tile shapes (128 or 256 pixels per CTA, and the cta_group::2 CTA pair) must give the same answers."""
     from dmvae_b200 import _lib
     _lib.query("dmvae_conv_tc_set_tile_mode", mode)
     try:
