@@ -803,7 +803,7 @@ int launch_conv_tc2(const void* x, const void* w, const float* bias, const void*
 
 // 0 = let the heuristic decide, 1 / 2 = force the number of 128-pixel sub-tiles per CTA, 3 = force CTA pairs
 int g_force_mt = 0;
-int g_pair_default = 0;      // flipped to 1 once the pair kernel is validated on hardware (dmvae_conv_tc_set_tile_mode(4))
+int g_pair_default = 1;      // CTA pairs for the N = 256 tiles (measured +10..30 % over the single-CTA tiles); mode 5 turns it off
 
 }  // namespace
 
@@ -841,7 +841,7 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     if (g_force_mt == 1) mt = 1;
     if (g_force_mt == 2 && bn >= 128 && pick_pixel_tile_n(H, W, 2 * BM, &bw2, &bh2)) mt = 2;
     // CTA pairs: 128-pixel tiles per CTA, an even number of them, full N tiles
-    if (bn >= 128 && Cout % bn == 0 && (g_force_mt == 3 || (g_force_mt == 0 && g_pair_default))) {
+    if (bn >= 128 && Cout % bn == 0 && (g_force_mt == 3 || (g_force_mt == 0 && g_pair_default && bn == 256))) {
         TcGeom gp = g;
         if (pick_pixel_tile_n(H, W, BM, &gp.BW, &gp.BH)) {
             gp.tiles_w = W / gp.BW; gp.tiles_h = H / gp.BH;
