@@ -32,7 +32,7 @@ SIGNATURES = {
     "dmvae_reparam_kl_bwd": [_p, _p, _p, _p, _p, _f, _i64, _i64, _i, _p],
     "dmvae_gn_stats": [_p, _p, _i64, _i64, _i, _p],
     "dmvae_gn_apply": [_p, _p, _p, _p, _p, _i64, _i64, _i, _f, _i, _p],
-    "dmvae_gn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _i, _p],
+    "dmvae_gn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _i, _p],
     "dmvae_pack_weights": [_p, _p, _p, _i, _i, _i, _i, _p],
     "dmvae_conv_tc_supported": [_i] * 7,
     "dmvae_conv_tc_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],

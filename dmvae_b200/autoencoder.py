@@ -76,7 +76,7 @@ class AttnBlock(_PackMixin, nn.Module):
 
     def _forward_cl(self, x: Tensor) -> Tensor:
         B, H, W, c = x.shape
-        h = _gn(self.norm, x, False)
+        h, x = ops.group_norm_silu_skip(x, self.norm.weight, self.norm.bias, False)
         q = _conv(self, "q", self.q, h, 1, (0, 0)).view(B, H * W, c)        # "b c h w -> b 1 (h w) c" is free here
         k = _conv(self, "k", self.k, h, 1, (0, 0)).view(B, H * W, c)
         v = _conv(self, "v", self.v, h, 1, (0, 0)).view(B, H * W, c)
@@ -102,7 +102,8 @@ class ResnetBlock(_PackMixin, nn.Module):
             self.nin_shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=1)
 
     def _forward_cl(self, x: Tensor) -> Tensor:
-        h = _conv(self, "conv1", self.conv1, _gn(self.norm1, x, True))
+        a1, x = ops.group_norm_silu_skip(x, self.norm1.weight, self.norm1.bias, True)   # x: residual branch
+        h = _conv(self, "conv1", self.conv1, a1)
         h = _gn(self.norm2, h, True)
         if self.in_channels != self.out_channels:
             x = _conv(self, "nin_shortcut", self.nin_shortcut, x, 1, (0, 0))

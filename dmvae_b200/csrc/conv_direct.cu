@@ -256,6 +256,73 @@ __global__ void __launch_bounds__(256) conv_thin_wgrad_kernel(const bf16* __rest
     }
 }
 
+// ---- weight gradient of the 3-channel head (conv_out, Cout = 3): sliding 3x3 window of x in registers ----------
+// Each thread owns one input channel and walks along an image row keeping the 3x3 neighbourhood of x for that channel in
+// registers (3 coalesced loads per step); dy for the row block sits in shared memory as float4 and is read by warp
+// broadcast.  27 FMAs + 3 loads + 1 LDS.128 per (pixel, channel).   dw[co][ci][kh][kw] += dy[q][co] * x[q + (kh-1, kw-1)][ci]
+__global__ void __launch_bounds__(256) conv_head_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                              float* __restrict__ dw, int B, int H, int W, int Cin, int rpb) {
+    extern __shared__ float4 s_dy[];              // [rows][W] {d0, d1, d2, 0}
+    const int blocks_per_img = (H + rpb - 1) / rpb;
+    const int b = blockIdx.x / blocks_per_img;
+    const int r0 = (blockIdx.x % blocks_per_img) * rpb;
+    const int r1 = min(r0 + rpb, H);
+    for (int i = threadIdx.x; i < (r1 - r0) * W; i += blockDim.x) {
+        const bf16* p = dy + (((int64_t)b * H + r0) * W + i) * 3;
+        s_dy[i] = make_float4(__bfloat162float(p[0]), __bfloat162float(p[1]), __bfloat162float(p[2]), 0.f);
+    }
+    __syncthreads();
+    const int parts = blockDim.x / Cin;           // column ranges handled in parallel (Cin <= blockDim.x)
+    const int ci = threadIdx.x % Cin, part = threadIdx.x / Cin;
+    float acc[3][3][3];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) (&acc[0][0][0])[i] = 0.f;
+    if (part < parts) {
+        const int ws = (int)((int64_t)W * part / parts), we = (int)((int64_t)W * (part + 1) / parts);
+        for (int r = r0; r < r1; ++r) {
+            const bf16* rowp[3];
+            bool rok[3];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int rr = r + kh - 1;
+                rok[kh] = rr >= 0 && rr < H;
+                rowp[kh] = x + (((int64_t)b * H + (rok[kh] ? rr : 0)) * W) * Cin + ci;
+            }
+            float win[3][2];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                win[kh][0] = (rok[kh] && ws - 1 >= 0) ? __bfloat162float(rowp[kh][(int64_t)(ws - 1) * Cin]) : 0.f;
+                win[kh][1] = rok[kh] ? __bfloat162float(rowp[kh][(int64_t)ws * Cin]) : 0.f;
+            }
+            const float4* drow = s_dy + (r - r0) * W;
+            for (int w = ws; w < we; ++w) {
+                float nx[3];
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+                    nx[kh] = (rok[kh] && w + 1 < W) ? __bfloat162float(rowp[kh][(int64_t)(w + 1) * Cin]) : 0.f;
+                const float4 d = drow[w];
+                const float dv[3] = {d.x, d.y, d.z};
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const float xs[3] = {win[kh][0], win[kh][1], nx[kh]};
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                        for (int co = 0; co < 3; ++co) acc[kh][kw][co] = fmaf(dv[co], xs[kw], acc[kh][kw][co]);
+                    win[kh][0] = win[kh][1];
+                    win[kh][1] = nx[kh];
+                }
+            }
+        }
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                for (int co = 0; co < 3; ++co) atomicAdd(&dw[((int64_t)co * Cin + ci) * 9 + kh * 3 + kw], acc[kh][kw][co]);
+    }
+}
+
 static int check_geom(const ConvGeom& g, const char* who) {
     if (g.B < 0 || g.H <= 0 || g.W <= 0 || g.Cin <= 0 || g.Cout <= 0 || g.KH <= 0 || g.KW <= 0 || g.stride <= 0)
         return dmvae_set_error(DMVAE_EINVAL, "%s: bad geometry", who);
@@ -478,6 +545,13 @@ DMVAE_API int dmvae_conv_direct_wgrad(const void* x, const void* dy, float* dw, 
         const int rpb = 8;
         const size_t smem = (size_t)(rpb + 2) * W * 3 * sizeof(float);
         const int blocks = B * ((H + rpb - 1) / rpb);
+        if (Cout == 3 && 256 % Cin == 0 && (size_t)rpb * W * sizeof(float4) <= 96 * 1024) {
+            const size_t smem4 = (size_t)rpb * W * sizeof(float4);
+            cudaFuncSetAttribute(conv_head_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            conv_head_wgrad_kernel<<<blocks, 256, smem4, st>>>((const bf16*)x, (const bf16*)dy, dw, B, H, W, Cin, rpb);
+            DMVAE_CHECK_LAUNCH("conv_head_wgrad_kernel");
+            return DMVAE_OK;
+        }
         if (Cout == 3) {
             cudaFuncSetAttribute(conv_thin_wgrad_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
             conv_thin_wgrad_kernel<3, true><<<blocks, 256, smem, st>>>((const bf16*)x, (const bf16*)dy, dw, B, H, W, Cin, rpb);

@@ -223,7 +223,8 @@ template <bool SILU>
 __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
     const bf16* __restrict__ da, const bf16* __restrict__ x, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ gsum,
-    const bf16* __restrict__ dres, bf16* __restrict__ dx, int64_t HW, int C, int vc, int rows, int64_t ppb, float eps) {
+    const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ colsum, int64_t HW, int C, int vc, int rows,
+    int64_t ppb, float eps) {
     extern __shared__ float s_mem[];   // a[C] b[C] k0[C] k1[C]
     float* s_a = s_mem; float* s_b = s_mem + C; float* s_k0 = s_mem + 2 * C; float* s_k1 = s_mem + 3 * C;
     const int b = blockIdx.y;
@@ -242,11 +243,11 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
     }
     __syncthreads();
     const int col = threadIdx.x % vc, row = threadIdx.x / vc;
-    float ca[8], cb[8], k0[8], k1[8];
+    float ca[8], cb[8], k0[8], k1[8], cs[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = col * 8 + k;
-        ca[k] = s_a[c]; cb[k] = s_b[c]; k0[k] = s_k0[c]; k1[k] = s_k1[c];
+        ca[k] = s_a[c]; cb[k] = s_b[c]; k0[k] = s_k0[c]; k1[k] = s_k1[c]; cs[k] = 0.f;
     }
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
@@ -275,8 +276,24 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
                 const float dy = gn_dy<SILU>(fd[k], fmaf(fx[k], ca[k], cb[k]));
                 fx[k] = fmaf(ca[k], dy, fmaf(k1[k], fx[k], k0[k])) + fr[k];
             }
-            st_stream16(dx + off + pp * C, pack_bf16x8(fx));
+            const uint4 packed = pack_bf16x8(fx);
+            st_stream16(dx + off + pp * C, packed);
+            if (colsum) {                       // column sums of the bf16 values written: the bias gradient of the conv that made x
+                float fo[8];
+                unpack_bf16x8(packed, fo);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cs[k] += fo[k];
+            }
         }
+    }
+    if (colsum) {
+        __syncthreads();                        // coefficient arrays are dead: reuse s_a as the fan-in buffer
+        for (int c = threadIdx.x; c < C; c += GN_THREADS) s_a[c] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&s_a[col * 8 + k], cs[k]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += GN_THREADS) atomicAdd(&colsum[c], s_a[c]);
     }
 }
 
@@ -316,8 +333,8 @@ DMVAE_API int dmvae_gn_apply(const void* x, const double* stats, const float* ga
 
 // gsum (fp64 [B][32][2]), dgamma, dbeta (fp32 [C]) are accumulated into: caller zero-initialises.
 DMVAE_API int dmvae_gn_bwd(const void* da, const void* x, const double* stats, const float* gamma, const float* beta,
-                           double* gsum, float* dgamma, float* dbeta, const void* dres, void* dx, int64_t B,
-                           int64_t HW, int C, float eps, int silu, void* stream) {
+                           double* gsum, float* dgamma, float* dbeta, const void* dres, void* dx, float* dx_colsum,
+                           int64_t B, int64_t HW, int C, float eps, int silu, void* stream) {
     DMVAE_CHECK_ARG(da && x && stats && gamma && beta && gsum && dgamma && dbeta && dx, "gn_bwd: null pointer");
     DMVAE_CHECK_ARG(B >= 0 && HW >= 0, "gn_bwd: negative size");
     DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)da & 15) == 0 && ((uintptr_t)dx & 15) == 0 &&
@@ -334,11 +351,11 @@ DMVAE_API int dmvae_gn_bwd(const void* da, const void* x, const double* stats, c
     if (silu) {
         gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem_r, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
         DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");
-        gn_bwd_apply_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, HW, C, g.vc, g.rows, ppb, eps);
+        gn_bwd_apply_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, dx_colsum, HW, C, g.vc, g.rows, ppb, eps);
     } else {
         gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem_r, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
         DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");
-        gn_bwd_apply_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, HW, C, g.vc, g.rows, ppb, eps);
+        gn_bwd_apply_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, dx_colsum, HW, C, g.vc, g.rows, ppb, eps);
     }
     DMVAE_CHECK_LAUNCH("gn_bwd_apply_kernel");
     return DMVAE_OK;

@@ -136,15 +136,31 @@ def gn_apply_raw(x, stats, gamma, beta, silu: bool, eps: float = GN_EPS) -> torc
     return y
 
 
-def gn_bwd_raw(da, x, stats, gamma, beta, silu: bool, dres=None, eps: float = GN_EPS):
+def gn_bwd_raw(da, x, stats, gamma, beta, silu: bool, dres=None, eps: float = GN_EPS, want_colsum: bool = False):
     B, H, W, c = x.shape
     gsum = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
-    dgamma = torch.zeros((c,), dtype=torch.float32, device=x.device)
-    dbeta = torch.zeros((c,), dtype=torch.float32, device=x.device)
+    # one zero-filled fp32 buffer for dgamma | dbeta | column sums
+    small = torch.zeros((3, c), dtype=torch.float32, device=x.device)
+    dgamma, dbeta, colsum = small[0], small[1], small[2]
     dx = torch.empty_like(x)
     call("dmvae_gn_bwd", ptr(da), ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(gsum), ptr(dgamma), ptr(dbeta), ptr(dres),
-         ptr(dx), B, H * W, c, eps, int(silu))
+         ptr(dx), ptr(colsum) if want_colsum else None, B, H * W, c, eps, int(silu))
+    if want_colsum:
+        _tag_colsum(dx, colsum)
     return dx, dgamma, dbeta
+
+
+def _tag_colsum(t: torch.Tensor, colsum: torch.Tensor) -> None:
+    """Side channel from the kernel that produced a gradient tensor to the conv backward that consumes it: the
+    per-channel sum over pixels (= that conv's bias gradient) was accumulated while the tensor was written."""
+    t._dmvae_colsum = (colsum, t.data_ptr(), tuple(t.shape))
+
+
+def _tagged_colsum(t: torch.Tensor) -> Optional[torch.Tensor]:
+    tag = getattr(t, "_dmvae_colsum", None)
+    if tag is not None and tag[1] == t.data_ptr() and tag[2] == tuple(t.shape):
+        return tag[0]
+    return None
 
 
 # ------------------------------------------------------------------------------------------------ autograd
@@ -176,7 +192,9 @@ class ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = conv_wgrad_raw(x, dy, kh, kw, stride, pad_tl)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = bias_grad_raw(dy)
+            db = _tagged_colsum(dy)                 # already reduced by the kernel that wrote dy (gn_bwd)
+            if db is None:
+                db = bias_grad_raw(dy)
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
         return dx, dw, db, dres, None, None, None, None
@@ -199,7 +217,33 @@ class GroupNormSiluFn(torch.autograd.Function):
     def backward(ctx, da):
         x, stats, g, b = ctx.saved_tensors
         da = _chk_nhwc(da, "group_norm backward")
-        dx, dgamma, dbeta = gn_bwd_raw(da, x, stats, g, b, ctx.silu)
+        dx, dgamma, dbeta = gn_bwd_raw(da, x, stats, g, b, ctx.silu, want_colsum=True)
+        return dx, dgamma, dbeta, None
+
+
+class GroupNormSiluSkipFn(torch.autograd.Function):
+    """(swish(GroupNorm(x)), x): the second output is the residual branch of ResnetBlock / AttnBlock
+    (models/flux_ae.py:52,82).  Returning it from the same node lets backward fold the gradient arriving over the
+    skip connection into the GroupNorm backward kernel (no separate add pass)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, silu: bool):
+        x = _chk_nhwc(x, "group_norm")
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        stats = gn_stats_raw(x)
+        y = gn_apply_raw(x, stats, g, b, silu)
+        ctx.silu = silu
+        ctx.save_for_backward(x, stats, g, b)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, da, dskip):
+        x, stats, g, b = ctx.saved_tensors
+        if da is None:                       # only the skip branch was used
+            return dskip, None, None, None
+        da = _chk_nhwc(da, "group_norm backward")
+        dres = None if dskip is None else _chk_nhwc(dskip, "group_norm skip gradient")
+        dx, dgamma, dbeta = gn_bwd_raw(da, x, stats, g, b, ctx.silu, dres=dres, want_colsum=True)
         return dx, dgamma, dbeta, None
 
 
@@ -310,6 +354,11 @@ def conv2d(x, weight, bias, pack: WeightPack, stride: int = 1, pad_tl=(1, 1), re
 
 def group_norm_silu(x, gamma, beta, silu: bool = True):
     return GroupNormSiluFn.apply(x, gamma, beta, silu)
+
+
+def group_norm_silu_skip(x, gamma, beta, silu: bool = True):
+    """Returns (activation, x_for_the_residual_branch)."""
+    return GroupNormSiluSkipFn.apply(x, gamma, beta, silu)
 
 
 def upsample2x(x):

@@ -95,11 +95,12 @@ int dmvae_gn_stats(const void* x, double* stats, int64_t B, int64_t HW, int C, v
 /* y = [swish]((x-mean)*rstd*gamma+beta) rounded to bf16. */
 int dmvae_gn_apply(const void* x, const double* stats, const float* gamma, const float* beta, void* y, int64_t B,
                    int64_t HW, int C, float eps, int silu, void* stream);
-/* backward of the above: dx (+= dres if given), dgamma/dbeta (fp32 [C], accumulated), gsum = fp64 scratch
- * [B][32][2] (caller zeroes). */
+/* backward of the above: dx (+= dres if given: the gradient arriving over the residual branch, :82), dgamma/dbeta
+ * (fp32 [C], accumulated), gsum = fp64 scratch [B][32][2] (caller zeroes).  dx_colsum (optional, fp32 [C],
+ * accumulated) receives sum_pixels dx: the bias gradient of the conv whose output x is. */
 int dmvae_gn_bwd(const void* da, const void* x, const double* stats, const float* gamma, const float* beta,
-                 double* gsum, float* dgamma, float* dbeta, const void* dres, void* dx, int64_t B, int64_t HW,
-                 int C, float eps, int silu, void* stream);
+                 double* gsum, float* dgamma, float* dbeta, const void* dres, void* dx, float* dx_colsum,
+                 int64_t B, int64_t HW, int C, float eps, int silu, void* stream);
 
 /* ------------------------------------------------------------------ A1/A2: convolutions --------------------- */
 
