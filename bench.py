@@ -81,8 +81,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ algorithmic work per call
 def _work(name, a):
     """FLOPs for the conv entry points (2*M*N*K, bias/GN excluded -- SURVEY.md section 8(d)); 0 otherwise."""
-    if name == "dmvae_conv_tc_fwd":        # x, w, bias, res, y, B, H, W, Cin, Cout, KH, KW
-        B, H, W, cin, cout, kh, kw = a[5:12]
+    if name == "dmvae_conv_tc_fwd":        # x, w, bias, res, y, gn_stats, B, H, W, Cin, Cout, KH, KW
+        B, H, W, cin, cout, kh, kw = a[6:13]
         return 2.0 * B * H * W * cin * cout * kh * kw
     if name == "dmvae_conv_tc_wgrad":      # x, dy, dw, B, H, W, Cin, Cout, KH, KW
         B, H, W, cin, cout, kh, kw = a[3:10]

@@ -35,7 +35,7 @@ SIGNATURES = {
     "dmvae_gn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _i, _p],
     "dmvae_pack_weights": [_p, _p, _p, _i, _i, _i, _i, _p],
     "dmvae_conv_tc_supported": [_i] * 7,
-    "dmvae_conv_tc_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "dmvae_conv_tc_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "dmvae_conv_tc_set_tile_mode": [_i],
     "dmvae_conv_tc_wgrad_supported": [_i] * 7,
     "dmvae_conv_tc_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],

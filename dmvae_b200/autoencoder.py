@@ -52,8 +52,10 @@ class _PackMixin:
         return new
 
 
-def _conv(mod: "_PackMixin", name: str, conv: nn.Conv2d, x_cl: Tensor, stride=1, pad_tl=(1, 1), residual=None, pad_br=None) -> Tensor:
-    return ops.conv2d(x_cl, conv.weight, conv.bias, mod._pack(name), stride, pad_tl, residual, pad_br)
+def _conv(mod: "_PackMixin", name: str, conv: nn.Conv2d, x_cl: Tensor, stride=1, pad_tl=(1, 1), residual=None, pad_br=None,
+          gn_next=False) -> Tensor:
+    """gn_next: the output goes into a GroupNorm next, so let the conv epilogue produce its statistics."""
+    return ops.conv2d(x_cl, conv.weight, conv.bias, mod._pack(name), stride, pad_tl, residual, pad_br, gn_next)
 
 
 def _gn(norm: nn.GroupNorm, x_cl: Tensor, silu: bool) -> Tensor:
@@ -82,7 +84,7 @@ class AttnBlock(_PackMixin, nn.Module):
         v = _conv(self, "v", self.v, h, 1, (0, 0)).view(B, H * W, c)
         o = ops.single_head_attention(q, k, v)                              # single head, d = C (library GEMMs, 0.3% of FLOPs)
         o = o.reshape(B, H, W, c)
-        return _conv(self, "proj_out", self.proj_out, o, 1, (0, 0), residual=x)
+        return _conv(self, "proj_out", self.proj_out, o, 1, (0, 0), residual=x, gn_next=True)
 
     def forward(self, x: Tensor) -> Tensor:
         return _from_cl(self._forward_cl(_to_cl(x)))
@@ -103,11 +105,11 @@ class ResnetBlock(_PackMixin, nn.Module):
 
     def _forward_cl(self, x: Tensor) -> Tensor:
         a1, x = ops.group_norm_silu_skip(x, self.norm1.weight, self.norm1.bias, True)   # x: residual branch
-        h = _conv(self, "conv1", self.conv1, a1)
+        h = _conv(self, "conv1", self.conv1, a1, gn_next=True)
         h = _gn(self.norm2, h, True)
         if self.in_channels != self.out_channels:
             x = _conv(self, "nin_shortcut", self.nin_shortcut, x, 1, (0, 0))
-        return _conv(self, "conv2", self.conv2, h, residual=x)      # residual add fused into the conv epilogue
+        return _conv(self, "conv2", self.conv2, h, residual=x, gn_next=True)      # residual add fused into the conv epilogue
 
     def forward(self, x):
         return _from_cl(self._forward_cl(_to_cl(x)))
@@ -135,7 +137,7 @@ class Upsample(_PackMixin, nn.Module):
         self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
 
     def _forward_cl(self, x: Tensor) -> Tensor:
-        return _conv(self, "conv", self.conv, ops.upsample2x(x))
+        return _conv(self, "conv", self.conv, ops.upsample2x(x), gn_next=True)
 
     def forward(self, x: Tensor):
         return _from_cl(self._forward_cl(_to_cl(x)))
@@ -256,9 +258,9 @@ class Decoder(_PackMixin, nn.Module):
             zc = _to_cl(z)
         if isinstance(self.conv_in, nn.Sequential):         # post_init stem: Upsample(z) + 3x3
             h = self.conv_in[0]._forward_cl(zc)
-            h = _conv(self, "conv_in.1", self.conv_in[1], h)
+            h = _conv(self, "conv_in.1", self.conv_in[1], h, gn_next=True)
         else:
-            h = _conv(self, "conv_in", self.conv_in, zc)
+            h = _conv(self, "conv_in", self.conv_in, zc, gn_next=True)
         h = self.mid.block_1._forward_cl(h)
         h = self.mid.attn_1._forward_cl(h)
         h = self.mid.block_2._forward_cl(h)

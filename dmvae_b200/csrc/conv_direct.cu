@@ -295,11 +295,15 @@ __global__ void __launch_bounds__(256) conv_head_wgrad_kernel(const bf16* __rest
                 win[kh][1] = rok[kh] ? __bfloat162float(rowp[kh][(int64_t)ws * Cin]) : 0.f;
             }
             const float4* drow = s_dy + (r - r0) * W;
+            float nx[3];                                   // column w+1, loaded one iteration ahead of its use
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+                nx[kh] = (rok[kh] && ws + 1 < W) ? __bfloat162float(rowp[kh][(int64_t)(ws + 1) * Cin]) : 0.f;
             for (int w = ws; w < we; ++w) {
-                float nx[3];
+                float nn[3];                               // prefetch column w+2
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh)
-                    nx[kh] = (rok[kh] && w + 1 < W) ? __bfloat162float(rowp[kh][(int64_t)(w + 1) * Cin]) : 0.f;
+                    nn[kh] = (rok[kh] && w + 2 < W) ? __bfloat162float(rowp[kh][(int64_t)(w + 2) * Cin]) : 0.f;
                 const float4 d = drow[w];
                 const float dv[3] = {d.x, d.y, d.z};
 #pragma unroll
@@ -311,6 +315,7 @@ __global__ void __launch_bounds__(256) conv_head_wgrad_kernel(const bf16* __rest
                         for (int co = 0; co < 3; ++co) acc[kh][kw][co] = fmaf(dv[co], xs[kw], acc[kh][kw][co]);
                     win[kh][0] = win[kh][1];
                     win[kh][1] = nx[kh];
+                    nx[kh] = nn[kh];
                 }
             }
         }
@@ -542,7 +547,7 @@ DMVAE_API int dmvae_conv_direct_wgrad(const void* x, const void* dy, float* dw, 
     const int taps = KH * KW;
     const bool same3 = KH == 3 && KW == 3 && stride == 1 && pad_top == 1 && pad_left == 1 && OH == H && OW == W;
     if (same3 && (Cout == 3 || Cin == 3) && (Cout == 3 ? Cin : Cout) <= 256 && W <= 1024) {
-        const int rpb = 8;
+        const int rpb = 4;
         const size_t smem = (size_t)(rpb + 2) * W * 3 * sizeof(float);
         const int blocks = B * ((H + rpb - 1) / rpb);
         if (Cout == 3 && 256 % Cin == 0 && (size_t)rpb * W * sizeof(float4) <= 96 * 1024) {

@@ -116,8 +116,74 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- epilogue helpers
+// GroupNorm statistics of the tile being stored (sum, sum of squares per (image, group)) are reduced here -- per thread
+// over its 32 channels, across the warp's 32 pixels by shuffles, then one fp64 atomic per group -- so the following
+// GroupNorm needs no separate statistics pass over the activation (2 B/element of HBM traffic saved per GN).
+template <int CPG>   // channels per group inside a 32-channel chunk (CPG = 32 means the chunk lies in one group)
+__device__ __forceinline__ void chunk_group_stats(const float (&r)[32], double* __restrict__ st, int g0, int lane) {
+    constexpr int NG = 32 / CPG;
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+        float sm = 0.f, sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < CPG; ++e) { const float x = r[gi * CPG + e]; sm += x; sq = fmaf(x, x, sq); }
+        sm = warp_sum(sm);
+        sq = warp_sum(sq);
+        if (lane == 0) { atomicAdd(&st[(g0 + gi) * 2], (double)sm); atomicAdd(&st[(g0 + gi) * 2 + 1], (double)sq); }
+    }
+}
+
+// One 32-column chunk of one accumulator row: + bias, bf16 rounding, optional residual add, 64-byte store, optional stats.
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int n, int64_t pix, const float* __restrict__ bias,
+                                               const bf16* __restrict__ res, bf16* __restrict__ out, int Cout,
+                                               double* __restrict__ st /* stats of this image or null */, int cpg, int lane) {
+    bf16* op = out + pix * Cout + n;
+    const bf16* rp = res ? res + pix * Cout + n : nullptr;
+    if (n + 32 <= Cout && (Cout & 7) == 0) {
+        float r[32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
+            if (rp) {
+                float fr[8];
+                unpack_bf16x8(*reinterpret_cast<const uint4*>(rp + q * 8), fr);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];   // bf16 conv output, then bf16 add
+            }
+            const uint4 pk = pack_bf16x8(f);
+            *reinterpret_cast<uint4*>(op + q * 8) = pk;
+            if (st) {
+                float fo[8];
+                unpack_bf16x8(pk, fo);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[q * 8 + e] = fo[e];
+            }
+        }
+        if (st) {
+            switch (cpg) {
+                case 1: chunk_group_stats<1>(r, st, n, lane); break;
+                case 2: chunk_group_stats<2>(r, st, n / 2, lane); break;
+                case 4: chunk_group_stats<4>(r, st, n / 4, lane); break;
+                case 8: chunk_group_stats<8>(r, st, n / 8, lane); break;
+                case 16: chunk_group_stats<16>(r, st, n / 16, lane); break;
+                default: chunk_group_stats<32>(r, st, n / cpg, lane); break;
+            }
+        }
+    } else {
+        for (int e = 0; e < 32 && n + e < Cout; ++e) {
+            float f = __uint_as_float(v[e]) + (bias ? __ldg(bias + n + e) : 0.f);
+            if (rp) f = bf16_round(f) + __bfloat162float(rp[e]);
+            op[e] = __float2bfloat16_rn(f);
+        }
+    }
+}
+
 struct TcGeom {
     int B, H, W, Cin, Cout, KH, KW, pt, pl;
+    int cpg;               // Cout / 32 (GroupNorm group width) when output statistics are requested
     int BW, BH;            // pixel tile = BH rows x BW cols of one image (BH*BW = 128)
     int tiles_w, tiles_h;  // W/BW, H/BH
     int m_tiles, n_tiles, k_chunks;
@@ -141,7 +207,8 @@ template <int BN, int MT> struct Cfg {
 template <int BN, int MT>
 __global__ void __launch_bounds__(Cfg<BN, MT>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out, TcGeom g) {
+               const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out,
+               double* __restrict__ stats, TcGeom g) {
     using C = Cfg<BN, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -246,29 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tmem_ld32(taddr + c0, v);
                 const int n = n0 + c0;
                 if (n >= g.Cout) continue;                            // warp-uniform
-                bf16* op = out + pix * g.Cout + n;
-                const bf16* rp = res ? res + pix * g.Cout + n : nullptr;
-                if (n + 32 <= g.Cout && (g.Cout & 7) == 0) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
-                        if (rp) {
-                            float fr[8];
-                            unpack_bf16x8(*reinterpret_cast<const uint4*>(rp + q * 8), fr);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];   // bf16 conv output, then bf16 add
-                        }
-                        *reinterpret_cast<uint4*>(op + q * 8) = pack_bf16x8(f);
-                    }
-                } else {
-                    for (int e = 0; e < 32 && n + e < g.Cout; ++e) {
-                        float f = __uint_as_float(v[e]) + (bias ? __ldg(bias + n + e) : 0.f);
-                        if (rp) f = bf16_round(f) + __bfloat162float(rp[e]);
-                        op[e] = __float2bfloat16_rn(f);
-                    }
-                }
+                epilogue_chunk(v, n, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -354,7 +399,8 @@ template <int BN> struct Cfg2 {
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out, TcGeom g) {
+                const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out,
+                double* __restrict__ stats, TcGeom g) {
     using C = Cfg2<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -455,29 +501,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tmem_ld32(taddr + c0, v);
                 const int n = n0 + c0;
                 if (n >= g.Cout) continue;
-                bf16* op = out + pix * g.Cout + n;
-                const bf16* rp = res ? res + pix * g.Cout + n : nullptr;
-                if (n + 32 <= g.Cout && (g.Cout & 7) == 0) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
-                        if (rp) {
-                            float fr[8];
-                            unpack_bf16x8(*reinterpret_cast<const uint4*>(rp + q * 8), fr);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];
-                        }
-                        *reinterpret_cast<uint4*>(op + q * 8) = pack_bf16x8(f);
-                    }
-                } else {
-                    for (int e = 0; e < 32 && n + e < g.Cout; ++e) {
-                        float f = __uint_as_float(v[e]) + (bias ? __ldg(bias + n + e) : 0.f);
-                        if (rp) f = bf16_round(f) + __bfloat162float(rp[e]);
-                        op[e] = __float2bfloat16_rn(f);
-                    }
-                }
+                epilogue_chunk(v, n, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -752,7 +776,7 @@ int num_sms() {
 }
 
 template <int BN, int MT>
-int launch_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, TcGeom g, cudaStream_t st) {
+int launch_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, double* stats, TcGeom g, cudaStream_t st) {
     using C = Cfg<BN, MT>;
     CUtensorMap ma, mb;
     const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
@@ -771,13 +795,13 @@ int launch_conv_tc(const void* x, const void* w, const float* bias, const void* 
     }
     const int tiles = g.m_tiles * g.n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    conv_tc_kernel<BN, MT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, g);
+    conv_tc_kernel<BN, MT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, stats, g);
     DMVAE_CHECK_LAUNCH("conv_tc_kernel");
     return DMVAE_OK;
 }
 
 template <int BN>
-int launch_conv_tc2(const void* x, const void* w, const float* bias, const void* res, void* y, TcGeom g, cudaStream_t st) {
+int launch_conv_tc2(const void* x, const void* w, const float* bias, const void* res, void* y, double* stats, TcGeom g, cudaStream_t st) {
     using C = Cfg2<BN>;
     CUtensorMap ma, mb;
     const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
@@ -796,7 +820,7 @@ int launch_conv_tc2(const void* x, const void* w, const float* bias, const void*
     }
     const int pair_tiles = (g.m_tiles / 2) * g.n_tiles;
     const int clusters = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
-    conv_tc2_kernel<BN><<<2 * clusters, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, g);
+    conv_tc2_kernel<BN><<<2 * clusters, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, stats, g);
     DMVAE_CHECK_LAUNCH("conv_tc2_kernel");
     return DMVAE_OK;
 }
@@ -819,7 +843,7 @@ DMVAE_API int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, in
 // stride-1 "same" convolution (3x3 pad 1 or 1x1 pad 0) on the tensor cores.
 //   y = conv(x, w_packed) + bias [; y = bf16(y) + residual]
 DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
-                                int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream) {
+                                double* gn_stats, int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream) {
     DMVAE_CHECK_ARG(x && w_packed && y, "conv_tc_fwd: null pointer");
     DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
                     ((uintptr_t)residual & 15) == 0, "conv_tc_fwd: buffers must be 16-byte aligned");
@@ -828,6 +852,16 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     TcGeom g;
     g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
     g.pt = (KH - 1) / 2; g.pl = (KW - 1) / 2;
+    double* stats = nullptr;
+    g.cpg = 0;
+    if (gn_stats) {
+        // fused GroupNorm(32) statistics need whole 32-channel chunks that do not straddle groups
+        const int cpg = Cout / 32;
+        if (Cout % 32 != 0 || !(cpg == 1 || cpg == 2 || cpg == 4 || cpg == 8 || cpg == 16 || cpg % 32 == 0))
+            return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_tc_fwd: fused GroupNorm statistics unsupported for Cout=%d", Cout);
+        stats = gn_stats;
+        g.cpg = cpg;
+    }
     g.k_chunks = (Cin + BK - 1) / BK;
     cudaStream_t st = (cudaStream_t)stream;
     const int bn = Cout <= 32 ? 32 : ((Cout % 256 == 0 || Cout > 256) ? 256 : 128);
@@ -847,19 +881,19 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
             gp.tiles_w = W / gp.BW; gp.tiles_h = H / gp.BH;
             gp.m_tiles = B * gp.tiles_w * gp.tiles_h;
             if (gp.m_tiles % 2 == 0 && (g_force_mt == 3 || (gp.m_tiles / 2) * gp.n_tiles >= (num_sms() * 3) / 8)) {
-                return bn == 256 ? launch_conv_tc2<256>(x, w_packed, bias, residual, y, gp, st)
-                                 : launch_conv_tc2<128>(x, w_packed, bias, residual, y, gp, st);
+                return bn == 256 ? launch_conv_tc2<256>(x, w_packed, bias, residual, y, stats, gp, st)
+                                 : launch_conv_tc2<128>(x, w_packed, bias, residual, y, stats, gp, st);
             }
         }
     }
     pick_pixel_tile_n(H, W, mt * BM, &g.BW, &g.BH);
     g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
     g.m_tiles = B * g.tiles_w * g.tiles_h;
-    if (bn == 32) return launch_conv_tc<32, 1>(x, w_packed, bias, residual, y, g, st);
-    if (bn == 256) return mt == 2 ? launch_conv_tc<256, 2>(x, w_packed, bias, residual, y, g, st)
-                                  : launch_conv_tc<256, 1>(x, w_packed, bias, residual, y, g, st);
-    return mt == 2 ? launch_conv_tc<128, 2>(x, w_packed, bias, residual, y, g, st)
-                   : launch_conv_tc<128, 1>(x, w_packed, bias, residual, y, g, st);
+    if (bn == 32) return launch_conv_tc<32, 1>(x, w_packed, bias, residual, y, stats, g, st);
+    if (bn == 256) return mt == 2 ? launch_conv_tc<256, 2>(x, w_packed, bias, residual, y, stats, g, st)
+                                  : launch_conv_tc<256, 1>(x, w_packed, bias, residual, y, stats, g, st);
+    return mt == 2 ? launch_conv_tc<128, 2>(x, w_packed, bias, residual, y, stats, g, st)
+                   : launch_conv_tc<128, 1>(x, w_packed, bias, residual, y, stats, g, st);
 }
 
 namespace {

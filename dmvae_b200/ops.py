@@ -60,7 +60,7 @@ class WeightPack:
 def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
                      kh: int, kw: int, stride: int = 1, pad_tl: Tuple[int, int] = (1, 1),
                      out_hw: Optional[Tuple[int, int]] = None, force_direct: bool = False,
-                     pad_br: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                     pad_br: Optional[Tuple[int, int]] = None, want_gn_stats: bool = False) -> torch.Tensor:
     """y = conv(x, w_packed[tap][Cout][Cin]) + bias (+ residual).  Picks the tcgen05 tile when the shape allows.
     pad_tl / pad_br: zero padding (top, left) / (bottom, right); pad_br defaults to pad_tl."""
     B, H, W, cin = x.shape
@@ -76,7 +76,12 @@ def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[tor
         bias = bias.float()
     same = stride == 1 and OH == H and OW == W and pt == (kh - 1) // 2 and pl == (kw - 1) // 2
     if same and not force_direct and query("dmvae_conv_tc_supported", B, H, W, cin, cout, kh, kw):
-        call("dmvae_conv_tc_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, cout, kh, kw)
+        stats = None
+        if want_gn_stats and cout % 32 == 0 and (cout // 32 in (1, 2, 4, 8, 16) or (cout // 32) % 32 == 0):
+            stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
+        call("dmvae_conv_tc_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), ptr(stats), B, H, W, cin, cout, kh, kw)
+        if stats is not None:
+            y._dmvae_gnstats = (stats, y.data_ptr(), tuple(y.shape))       # consumed by the next GroupNorm
     else:
         call("dmvae_conv_direct_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, OH, OW, cout,
              kh, kw, stride, pt, pl)
@@ -120,6 +125,13 @@ def bias_grad_raw(dy: torch.Tensor) -> torch.Tensor:
     db = torch.zeros((c,), dtype=torch.float32, device=dy.device)
     call("dmvae_bias_grad", ptr(dy), ptr(db), dy.numel() // c, c)
     return db
+
+
+def _tagged_gn_stats(x: torch.Tensor) -> Optional[torch.Tensor]:
+    tag = getattr(x, "_dmvae_gnstats", None)
+    if tag is not None and tag[1] == x.data_ptr() and tag[2] == tuple(x.shape):
+        return tag[0]
+    return None
 
 
 def gn_stats_raw(x: torch.Tensor) -> torch.Tensor:
@@ -168,13 +180,14 @@ class ConvFn(torch.autograd.Function):
     """nn.Conv2d on channels-last bf16 (models/flux_ae.py:32-35,63,65,67,89,101,133,158,210,237,274)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, pack: WeightPack, stride: int, pad_tl, pad_br=None):
+    def forward(ctx, x, weight, bias, residual, pack: WeightPack, stride: int, pad_tl, pad_br=None, want_gn_stats=False):
         x = _chk_nhwc(x, "conv")
         cout, cin, kh, kw = weight.shape
         w_fwd, w_dgrad = pack.get(weight)
         if residual is not None:
             residual = _chk_nhwc(residual, "conv residual")
-        y = conv_forward_raw(x, w_fwd, None if bias is None else bias.detach(), residual, kh, kw, stride, pad_tl, pad_br=pad_br)
+        y = conv_forward_raw(x, w_fwd, None if bias is None else bias.detach(), residual, kh, kw, stride, pad_tl, pad_br=pad_br,
+                             want_gn_stats=want_gn_stats)
         ctx.geom = (kh, kw, stride, pad_tl, x.shape[1:3])
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
@@ -197,7 +210,7 @@ class ConvFn(torch.autograd.Function):
                 db = bias_grad_raw(dy)
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
-        return dx, dw, db, dres, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None
 
 
 class GroupNormSiluFn(torch.autograd.Function):
@@ -207,7 +220,9 @@ class GroupNormSiluFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, silu: bool):
         x = _chk_nhwc(x, "group_norm")
         g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        stats = gn_stats_raw(x)
+        stats = _tagged_gn_stats(x)                   # already reduced by the conv epilogue that wrote x
+        if stats is None:
+            stats = gn_stats_raw(x)
         y = gn_apply_raw(x, stats, g, b, silu)
         ctx.silu = silu
         ctx.save_for_backward(x, stats, g, b)
@@ -230,7 +245,9 @@ class GroupNormSiluSkipFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, silu: bool):
         x = _chk_nhwc(x, "group_norm")
         g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        stats = gn_stats_raw(x)
+        stats = _tagged_gn_stats(x)
+        if stats is None:
+            stats = gn_stats_raw(x)
         y = gn_apply_raw(x, stats, g, b, silu)
         ctx.silu = silu
         ctx.save_for_backward(x, stats, g, b)
@@ -348,8 +365,10 @@ def single_head_attention(q, k, v):
     return SingleHeadAttentionFn.apply(q, k, v)
 
 
-def conv2d(x, weight, bias, pack: WeightPack, stride: int = 1, pad_tl=(1, 1), residual=None, pad_br=None):
-    return ConvFn.apply(x, weight, bias, residual, pack, stride, pad_tl, pad_br)
+def conv2d(x, weight, bias, pack: WeightPack, stride: int = 1, pad_tl=(1, 1), residual=None, pad_br=None,
+           want_gn_stats: bool = False):
+    """want_gn_stats: the output feeds a GroupNorm(32): have the conv epilogue reduce its statistics."""
+    return ConvFn.apply(x, weight, bias, residual, pack, stride, pad_tl, pad_br, want_gn_stats)
 
 
 def group_norm_silu(x, gamma, beta, silu: bool = True):

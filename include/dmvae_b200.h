@@ -114,9 +114,11 @@ int dmvae_pack_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int
 int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW);
 
 /* tcgen05 implicit GEMM.  Replaces cuDNN conv forward for nn.Conv2d at models/flux_ae.py:32-35,63,65,67,101,210
- * and -- fed dY and w_dgrad -- cuDNN's backward-data.   y = conv(x) + bias ; if residual: y = bf16(y) + residual. */
+ * and -- fed dY and w_dgrad -- cuDNN's backward-data.   y = conv(x) + bias ; if residual: y = bf16(y) + residual.
+ * gn_stats (optional, fp64 [B][32][2], caller-zeroed): the epilogue also accumulates {sum y, sum y^2} per (image,
+ * GroupNorm group) of the stored bf16 values, i.e. the output of dmvae_gn_stats for the next GroupNorm(32). */
 int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
-                      int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
+                      double* gn_stats, int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
 
 /* Tuning / test hook (host only): 0 = heuristic, 1 = 128-pixel tiles per CTA, 2 = 256-pixel tiles where possible. */
 int dmvae_conv_tc_set_tile_mode(int mode);

@@ -301,6 +301,31 @@ def test_conv_tcgen05_tile_modes(case, mode):
         _lib.query("dmvae_conv_tc_set_tile_mode", 0)
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("cin,cout,hw,res", [(64, 128, 16, True), (128, 256, 16, False), (256, 512, 16, True), (64, 32, 16, False)])
+def test_conv_epilogue_group_norm_stats(cin, cout, hw, res, mode):
+    """The statistics the conv epilogue reduces must equal a separate gn_stats pass over the stored bf16 output."""
+    from dmvae_b200 import _lib
+    ops, _ = _ops()
+    g = torch.Generator(device=DEV).manual_seed(cout)
+    x = torch.randn(2, hw, hw, cin, generator=g, device=DEV).bfloat16()
+    w = torch.randn(cout, cin, 3, 3, generator=g, device=DEV) / math.sqrt(cin * 9)
+    b = torch.randn(cout, generator=g, device=DEV)
+    r = torch.randn(2, hw, hw, cout, generator=g, device=DEV).bfloat16() if res else None
+    wf, _wd = ops.WeightPack().get(w)
+    _lib.query("dmvae_conv_tc_set_tile_mode", mode)
+    try:
+        y = ops.conv_forward_raw(x, wf, b, r, 3, 3, want_gn_stats=True)
+    finally:
+        _lib.query("dmvae_conv_tc_set_tile_mode", 0)
+    fused = ops._tagged_gn_stats(y)
+    assert fused is not None
+    ref = ops.gn_stats_raw(y)
+    torch.cuda.synchronize()
+    # same bf16 values, different fp32 partial-sum order: 1e-5 relative on sums of ~10^3..10^4 terms
+    assert torch.allclose(fused, ref, rtol=1e-5, atol=1e-3), (fused - ref).abs().max()
+
+
 def test_conv_tc_many_tiles_matches_direct():
     """Full-size layer (512->512 @64x64, B=2: 128 pixel tiles x 2 N tiles): tensor-core path vs CUDA-core path on device."""
     ops, _ = _ops()
