@@ -18,6 +18,11 @@ from . import _lib
 from ._lib import BF16, F32, call, ptr, query
 
 GN_EPS = 1e-6
+# The conv epilogue can reduce the next GroupNorm's statistics.  The cross-pixel warp reduction costs 10 shuffles per
+# group per 32-channel chunk, which only pays when groups are wide; below this group width the separate (HBM-bound)
+# gn_stats pass is cheaper (measured on B200: 16 -> channels >= 512).
+import os as _os
+FUSE_GN_STATS_MIN_CPG = int(_os.environ.get("DMVAE_FUSE_GN_STATS_MIN_CPG", "16"))
 
 
 def _chk_nhwc(x: torch.Tensor, name: str) -> torch.Tensor:
@@ -77,7 +82,8 @@ def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[tor
     same = stride == 1 and OH == H and OW == W and pt == (kh - 1) // 2 and pl == (kw - 1) // 2
     if same and not force_direct and query("dmvae_conv_tc_supported", B, H, W, cin, cout, kh, kw):
         stats = None
-        if want_gn_stats and cout % 32 == 0 and (cout // 32 in (1, 2, 4, 8, 16) or (cout // 32) % 32 == 0):
+        if want_gn_stats and cout % 32 == 0 and cout // 32 >= FUSE_GN_STATS_MIN_CPG and \
+                (cout // 32 in (1, 2, 4, 8, 16) or (cout // 32) % 32 == 0):
             stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
         call("dmvae_conv_tc_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), ptr(stats), B, H, W, cin, cout, kh, kw)
         if stats is not None:

@@ -314,9 +314,12 @@ def test_conv_epilogue_group_norm_stats(cin, cout, hw, res, mode):
     r = torch.randn(2, hw, hw, cout, generator=g, device=DEV).bfloat16() if res else None
     wf, _wd = ops.WeightPack().get(w)
     _lib.query("dmvae_conv_tc_set_tile_mode", mode)
+    old = ops.FUSE_GN_STATS_MIN_CPG
+    ops.FUSE_GN_STATS_MIN_CPG = 1           # exercise every group width
     try:
         y = ops.conv_forward_raw(x, wf, b, r, 3, 3, want_gn_stats=True)
     finally:
+        ops.FUSE_GN_STATS_MIN_CPG = old
         _lib.query("dmvae_conv_tc_set_tile_mode", 0)
     fused = ops._tagged_gn_stats(y)
     assert fused is not None
