@@ -57,10 +57,13 @@ class VAELossFunction:
         self.base_model = base_model
 
     def compute_distribution_matching_loss(self, latents_norm: torch.Tensor, labels: torch.Tensor, step: int = 0,
-                                           cpu_generator: Optional[torch.Generator] = None):
-        """train_dmd.py:204-230.  Returns (loss, log) with device-side scalars in ``log`` (no host sync here)."""
+                                           cpu_generator: Optional[torch.Generator] = None,
+                                           t: Optional[torch.Tensor] = None, x0: Optional[torch.Tensor] = None):
+        """train_dmd.py:204-230.  Returns (loss, log) with device-side scalars in ``log`` (no host sync here).
+        ``t`` / ``x0`` may be injected (what ``self.transport.sample`` returns in the reference) for reproducible tests."""
         a = self.args
-        t, x0 = sample_t_x0(latents_norm, a.time_dist_shift, cpu_generator=cpu_generator)
+        if t is None or x0 is None:
+            t, x0 = sample_t_x0(latents_norm, a.time_dist_shift, cpu_generator=cpu_generator)
         t = t * (a.t1 - a.t0) + a.t0
         xt = losses.dmd_mix_xt(latents_norm, x0, t)
         with torch.no_grad():
