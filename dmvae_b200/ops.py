@@ -87,7 +87,7 @@ def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[tor
             stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
         call("dmvae_conv_tc_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), ptr(stats), B, H, W, cin, cout, kh, kw)
         if stats is not None:
-            y._dmvae_gnstats = (stats, y.data_ptr(), tuple(y.shape), y._version)       # consumed by the next GroupNorm
+            y._dmvae_gnstats = (stats, y.data_ptr(), tuple(y.shape), _ver(y))       # consumed by the next GroupNorm
     else:
         call("dmvae_conv_direct_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, OH, OW, cout,
              kh, kw, stride, pt, pl)
@@ -135,7 +135,7 @@ def bias_grad_raw(dy: torch.Tensor) -> torch.Tensor:
 
 def _tagged_gn_stats(x: torch.Tensor) -> Optional[torch.Tensor]:
     tag = getattr(x, "_dmvae_gnstats", None)
-    if tag is not None and tag[1] == x.data_ptr() and tag[2] == tuple(x.shape) and tag[3] == x._version:
+    if tag is not None and tag[1] == x.data_ptr() and tag[2] == tuple(x.shape) and tag[3] == _ver(x):
         return tag[0]
     return None
 
@@ -168,15 +168,20 @@ def gn_bwd_raw(da, x, stats, gamma, beta, silu: bool, dres=None, eps: float = GN
     return dx, dgamma, dbeta
 
 
+def _ver(t: torch.Tensor) -> int:
+    """Version counter, or -1 for inference tensors (which cannot be modified in place outside inference mode)."""
+    return -1 if t.is_inference() else t._version
+
+
 def _tag_colsum(t: torch.Tensor, colsum: torch.Tensor) -> None:
     """Side channel from the kernel that produced a gradient tensor to the conv backward that consumes it: the
     per-channel sum over pixels (= that conv's bias gradient) was accumulated while the tensor was written."""
-    t._dmvae_colsum = (colsum, t.data_ptr(), tuple(t.shape), t._version)
+    t._dmvae_colsum = (colsum, t.data_ptr(), tuple(t.shape), _ver(t))
 
 
 def _tagged_colsum(t: torch.Tensor) -> Optional[torch.Tensor]:
     tag = getattr(t, "_dmvae_colsum", None)
-    if tag is not None and tag[1] == t.data_ptr() and tag[2] == tuple(t.shape) and tag[3] == t._version:
+    if tag is not None and tag[1] == t.data_ptr() and tag[2] == tuple(t.shape) and tag[3] == _ver(t):
         return tag[0]
     return None
 
