@@ -115,5 +115,12 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
     return u;
 }
 
+// sigmoid via one MUFU.TANH: 0.5*tanh(0.5x)+0.5, abs. error ~1.2e-4 -- used only where the result is a gradient factor
+// that is rounded to bf16 afterwards (GroupNorm/swish backward); the forward pass keeps the accurate form below.
+__device__ __forceinline__ float sigmoidf_tanh(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
 // sigmoid via MUFU.EX2 + MUFU.RCP (rel. error ~1e-6; no IEEE division sequence)
 __device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
 template <bool SILU>
 __device__ __forceinline__ float gn_dy(float da, float yv) {
     if (!SILU) return da;
-    const float sg = sigmoidf_fast(yv);
+    const float sg = sigmoidf_tanh(yv);
     return da * fmaf(yv * sg, 1.f - sg, sg);
 }
 

@@ -50,6 +50,25 @@ def init_weights(model: nn.Module, conv_std_or_gain: float = 0.02, other_std: fl
                 m.weight.data.fill_(1.0)
 
 
+def _frozen_cast(mod: nn.Module, name: str) -> torch.Tensor:
+    """Under autocast every Linear re-casts its fp32 weight to bf16 on every forward.  For frozen parameters (the
+    encoder in stage 1, train_tokenizer.py:295-297) the cast is cached on the module across steps; numerics unchanged."""
+    p = getattr(mod, name)
+    if p is None or p.requires_grad or not p.is_cuda or not torch.is_autocast_enabled():
+        return p
+    dt = torch.get_autocast_dtype("cuda")
+    cache = mod.__dict__.setdefault("_cast_cache", {})
+    hit = cache.get(name)
+    if hit is None or hit[0] != p._version or hit[1] != p.data_ptr() or hit[2].dtype != dt:
+        hit = (p._version, p.data_ptr(), p.detach().to(dt))
+        cache[name] = hit
+    return hit[2]
+
+
+def _linear(mod: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    return nn.functional.linear(x, _frozen_cast(mod, "weight"), _frozen_cast(mod, "bias"))
+
+
 class _Affine(nn.Module):
     """(x - a) / b or x * b + a with per-channel buffers named ``mean`` / ``std`` (models/vae.py:10-31)."""
 
@@ -81,9 +100,9 @@ class _Attn(nn.Module):
 
     def forward(self, x):
         B, N, D = x.shape
-        q, k, v = self.qkv(x).view(B, N, 3, self.heads, D // self.heads).permute(2, 0, 3, 1, 4)
+        q, k, v = _linear(self.qkv, x).view(B, N, 3, self.heads, D // self.heads).permute(2, 0, 3, 1, 4)
         o = nn.functional.scaled_dot_product_attention(q, k, v)
-        return self.proj(o.transpose(1, 2).reshape(B, N, D))
+        return _linear(self.proj, o.transpose(1, 2).reshape(B, N, D))
 
 
 class _Mlp(nn.Module):
@@ -93,7 +112,7 @@ class _Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden, dim)
 
     def forward(self, x):
-        return self.fc2(nn.functional.gelu(self.fc1(x)))
+        return _linear(self.fc2, nn.functional.gelu(_linear(self.fc1, x)))
 
 
 class _Gamma(nn.Module):
