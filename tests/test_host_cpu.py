@@ -94,12 +94,19 @@ g = torch.Generator().manual_seed(100)
 x_all = torch.randn(8, 8, generator=g)
 arena.zero()
 net(x_all[rank * 4:(rank + 1) * 4]).square().mean().backward()      # each rank: its shard of the images
+assert arena.overlap and any(arena._launched), "chunks must have been launched from the autograd hooks during backward"
 arena.allreduce()
 sharded = arena.flat.clone()
-arena.zero()
-net(x_all).square().mean().backward()                                   # the same 8 images on one rank
-assert torch.allclose(sharded, arena.flat, rtol=1e-5, atol=1e-7), (sharded - arena.flat).abs().max()
+# the same 8 images on one rank, without touching .grad (no hooks, no exchange)
+ref = torch.autograd.grad(net(x_all).square().mean(), list(net.parameters()))
+ref = torch.cat([g.reshape(-1) for g in ref])
+assert torch.allclose(sharded, ref, rtol=1e-5, atol=1e-7), (sharded - ref).abs().max()
 assert all(p.grad.data_ptr() >= arena.flat.data_ptr() for p in net.parameters())
+# a second step reuses the arena: zero(), backward, allreduce
+arena.zero()
+net(x_all[rank * 4:(rank + 1) * 4]).square().mean().backward()
+arena.allreduce()
+assert torch.allclose(arena.flat, ref, rtol=1e-5, atol=1e-7)
 dist.destroy_process_group()
 print("OK", rank)
 '''
