@@ -40,6 +40,7 @@ SIGNATURES = {
     "dmvae_conv_tc_wgrad_supported": [_i] * 7,
     "dmvae_conv_tc_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "dmvae_wgrad_unpack": [_p, _p, _i, _i, _i, _i, _p],
+    "dmvae_grad_patches": [_p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p],
     "dmvae_conv_direct_fwd": [_p, _p, _p, _p, _p] + [_i] * 12 + [_p],
     "dmvae_conv_direct_dgrad_strided": [_p, _p, _p] + [_i] * 12 + [_p],
     "dmvae_conv_direct_wgrad": [_p, _p, _p] + [_i] * 12 + [_p],

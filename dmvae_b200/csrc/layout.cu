@@ -244,3 +244,49 @@ DMVAE_API int dmvae_wgrad_unpack(const float* dw_tap_major, float* dw, int Cout,
     DMVAE_CHECK_LAUNCH("wgrad_unpack_kernel");
     return DMVAE_OK;
 }
+
+// ---- gradient patches of a thin output (the C->3 head) ---------------------------------------------------------------
+// P[pixel][j], j = tap*Cout + co  (padded with zeros to 32 columns):  P[p][j] = dy[p - offset(tap)][co], zero outside.
+// With it both gradients of a "same" conv with a handful of output channels become plain 1x1 GEMMs on the tcgen05 tiles:
+//   dx[p][ci]          = sum_j P[p][j] * Wm[j][ci]          (conv_tc_fwd, 1x1, Cin = 32)
+//   dw[(tap,co)][ci]   = sum_p P[p][j] * x[p][ci]           (conv_tc_wgrad, 1x1, "Cout" = 32)
+// instead of CUDA-core kernels that are bound by instruction issue (models/flux_ae.py:237 conv_out, 128 -> 3).
+__global__ void __launch_bounds__(256) grad_patches_kernel(const bf16* __restrict__ dy, bf16* __restrict__ P, int64_t B, int H, int W,
+                                                           int Cout, int KH, int KW, int pt, int pl) {
+    const int64_t n = B * H * W * 4;                       // 4 x 16-byte vectors per 32-column row
+    const int taps = KH * KW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i & 3);
+        int64_t p = i >> 2;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int64_t b = p / H;
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = v * 8 + k;
+            float val = 0.f;
+            if (j < taps * Cout) {
+                const int tap = j / Cout, co = j - tap * Cout;
+                // y[q] uses x[q + (kh - pt, kw - pl)]  =>  x[p] meets dy[q] with q = p - (kh - pt, kw - pl)
+                const int qh = h - (tap / KW - pt), qw = w - (tap % KW - pl);
+                if (qh >= 0 && qh < H && qw >= 0 && qw < W) val = __bfloat162float(dy[((b * H + qh) * W + qw) * Cout + co]);
+            }
+            f[k] = val;
+        }
+        *reinterpret_cast<uint4*>(P + (i << 3)) = pack_bf16x8(f);
+    }
+}
+
+DMVAE_API int dmvae_grad_patches(const void* dy, void* patches, int64_t B, int H, int W, int Cout, int KH, int KW, int pad_top,
+                                 int pad_left, void* stream) {
+    DMVAE_CHECK_ARG(dy && patches, "grad_patches: null pointer");
+    DMVAE_CHECK_ARG(B >= 0 && H > 0 && W > 0 && Cout > 0 && KH > 0 && KW > 0, "grad_patches: bad shape");
+    DMVAE_CHECK_ARG(KH * KW * Cout <= 32, "grad_patches: taps*Cout = %d exceeds 32", KH * KW * Cout);
+    DMVAE_CHECK_ARG(((uintptr_t)patches & 15) == 0, "grad_patches: output must be 16-byte aligned");
+    const int64_t n = B * H * W * 4;
+    if (n == 0) return DMVAE_OK;
+    grad_patches_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)patches, B, H, W, Cout, KH, KW, pad_top, pad_left);
+    DMVAE_CHECK_LAUNCH("grad_patches_kernel");
+    return DMVAE_OK;
+}

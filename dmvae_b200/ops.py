@@ -187,6 +187,36 @@ def _tagged_colsum(t: torch.Tensor) -> Optional[torch.Tensor]:
 
 
 # ------------------------------------------------------------------------------------------------ autograd
+def thin_output_grads(x: Optional[torch.Tensor], dy: torch.Tensor, w_fwd: torch.Tensor, kh: int, kw: int,
+                      pad_tl: Tuple[int, int], need_dx: bool, need_dw: bool):
+    """dx and dw of a stride-1 "same" conv with taps*Cout <= 32 (the 128 -> 3 head) as two 1x1 GEMMs on the tcgen05
+    tiles over the gradient-patch matrix P (see dmvae_grad_patches)."""
+    B, H, W, cout = dy.shape
+    taps, _, cin = w_fwd.shape                      # packed forward operand [tap][Cout][Cin] (bf16)
+    P = torch.empty((B, H, W, 32), dtype=torch.bfloat16, device=dy.device)
+    call("dmvae_grad_patches", ptr(dy), ptr(P), B, H, W, cout, kh, kw, pad_tl[0], pad_tl[1])
+    dx = dw = None
+    if need_dx:
+        # Wm[j = tap*Cout + co][ci] = w[co][ci][tap]  ->  packed 1x1 operand [1][Cout_gemm = cin][Cin_gemm = 32]
+        wm = torch.zeros((1, cin, 32), dtype=torch.bfloat16, device=dy.device)
+        wm[0, :, :taps * cout] = w_fwd.permute(2, 0, 1).reshape(cin, taps * cout)
+        dx = conv_forward_raw(P, wm, None, None, 1, 1, 1, (0, 0))
+    if need_dw:
+        scratch = torch.zeros((1, 32, cin), dtype=torch.float32, device=dy.device)     # [1 tap][32 "couts"][cin]
+        call("dmvae_conv_tc_wgrad", ptr(x), ptr(P), ptr(scratch), B, H, W, cin, 32, 1, 1)
+        dw = scratch[0, :taps * cout].reshape(taps, cout, cin).permute(1, 2, 0).reshape(cout, cin, kh, kw).contiguous()
+    return dx, dw
+
+
+def _thin_output_ok(dy: torch.Tensor, w_fwd: torch.Tensor, kh: int, kw: int, stride: int, pad_tl, in_hw) -> bool:
+    B, OH, OW, cout = dy.shape
+    cin = w_fwd.shape[2]
+    return (stride == 1 and (OH, OW) == tuple(in_hw) and kh * kw * cout <= 32 and pad_tl == ((kh - 1) // 2, (kw - 1) // 2)
+            and cin % 8 == 0 and cin >= 32
+            and bool(query("dmvae_conv_tc_supported", B, OH, OW, 32, cin, 1, 1))
+            and bool(query("dmvae_conv_tc_wgrad_supported", B, OH, OW, cin, 32, 1, 1)))
+
+
 class ConvFn(torch.autograd.Function):
     """nn.Conv2d on channels-last bf16 (models/flux_ae.py:32-35,63,65,67,89,101,133,158,210,237,274)."""
 
@@ -211,10 +241,13 @@ class ConvFn(torch.autograd.Function):
         kh, kw, stride, pad_tl, in_hw = ctx.geom
         dy = _chk_nhwc(dy, "conv backward")
         dx = dw = db = dres = None
-        if ctx.needs_input_grad[0]:
-            dx = conv_dgrad_raw(dy, w_fwd, w_dgrad, in_hw, kh, kw, stride, pad_tl)
-        if ctx.needs_input_grad[1]:
-            dw = conv_wgrad_raw(x, dy, kh, kw, stride, pad_tl)
+        if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _thin_output_ok(dy, w_fwd, kh, kw, stride, tuple(pad_tl), in_hw):
+            dx, dw = thin_output_grads(x, dy, w_fwd, kh, kw, tuple(pad_tl), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = conv_dgrad_raw(dy, w_fwd, w_dgrad, in_hw, kh, kw, stride, pad_tl)
+            if ctx.needs_input_grad[1]:
+                dw = conv_wgrad_raw(x, dy, kh, kw, stride, pad_tl)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _tagged_colsum(dy)                 # already reduced by the kernel that wrote dy (gn_bwd)
             if db is None:

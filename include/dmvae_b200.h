@@ -132,6 +132,12 @@ int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_major, int 
 int dmvae_wgrad_unpack(const float* dw_tap_major, float* dw, int Cout, int Cin, int taps, int accumulate,
                        void* stream);
 
+/* Gradient patches for convs with a handful of output channels (the C->3 head, :237): P[pixel][tap*Cout+co] (bf16, 32
+ * columns, zero padded) = dy[pixel - offset(tap)][co].  Both of that conv's gradients then run as 1x1 GEMMs on the tcgen05
+ * tiles (dmvae_conv_tc_fwd with Cin=32 for dx, dmvae_conv_tc_wgrad with Cout=32 for dw). */
+int dmvae_grad_patches(const void* dy, void* patches, int64_t B, int H, int W, int Cout, int KH, int KW, int pad_top,
+                       int pad_left, void* stream);
+
 /* CUDA-core path for the ragged layers (Cin=32 stem :272-275, Cout=3 head :237, Cin=3 encoder stem :133,
  * stride-2 Downsample :89-95) and the on-device cross-check of the tensor-core path. */
 int dmvae_conv_direct_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,

@@ -329,6 +329,28 @@ def test_conv_epilogue_group_norm_stats(cin, cout, hw, res, mode):
     assert torch.allclose(fused, ref, rtol=1e-5, atol=1e-3), (fused - ref).abs().max()
 
 
+def test_thin_head_gradients_as_gemms():
+    """conv_out (128 -> 3): dx and dw through the gradient-patch matrix + tcgen05 1x1 GEMMs vs the CUDA-core kernels."""
+    ops, _ = _ops()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    B, H, W, cin, cout = 2, 32, 64, 128, 3
+    x = torch.randn(B, H, W, cin, generator=g, device=DEV).bfloat16()
+    dy = torch.randn(B, H, W, cout, generator=g, device=DEV).bfloat16()
+    w = torch.randn(cout, cin, 3, 3, generator=g, device=DEV) / 34
+    wf, wd = ops.WeightPack().get(w)
+    assert ops._thin_output_ok(dy, wf, 3, 3, 1, (1, 1), (H, W))
+    dx, dw = ops.thin_output_grads(x, dy, wf, 3, 3, (1, 1), True, True)
+    dx_ref = ops.conv_dgrad_raw(dy, wf, wd, (H, W), 3, 3, force_direct=True)
+    dw_ref = ops.conv_wgrad_raw(x, dy, 3, 3, force_direct=True)
+    assert rel_err(dx.float(), dx_ref.float()) < 4e-3
+    assert rel_err(dw, dw_ref) < 1e-3
+    # and against the fp32 reference math
+    xr = x.float().permute(0, 3, 1, 2).cpu().requires_grad_(True)
+    wr = O.r16(w.cpu()).requires_grad_(True)
+    F.conv2d(xr, wr, None, padding=1).backward(dy.float().permute(0, 3, 1, 2).cpu())
+    assert rel_err(nchw(dx), xr.grad) < 4e-3 and rel_err(dw, wr.grad) < 1e-3
+
+
 def test_conv_tc_many_tiles_matches_direct():
     """Full-size layer (512->512 @64x64, B=2: 128 pixel tiles x 2 N tiles): tensor-core path vs CUDA-core path on device."""
     ops, _ = _ops()
