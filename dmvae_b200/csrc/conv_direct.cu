@@ -500,40 +500,6 @@ __global__ void __launch_bounds__(256) conv_direct_wgrad_kernel(const bf16* __re
     }
 }
 
-// Cout <= 4: threads own input channels, 9*CO accumulators each, x streamed once through L1
-template <int CO, int TAPS>
-__global__ void __launch_bounds__(128) conv_small_cout_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
-                                                                    float* __restrict__ dw, ConvGeom g, int64_t m_per_block) {
-    const int64_t M = (int64_t)g.B * g.OH * g.OW;
-    const int64_t ms = (int64_t)blockIdx.x * m_per_block;
-    const int64_t me = (ms + m_per_block < M) ? ms + m_per_block : M;
-    for (int ci = threadIdx.x; ci < g.Cin; ci += blockDim.x) {
-        float acc[TAPS][CO];
-#pragma unroll
-        for (int tp = 0; tp < TAPS; ++tp)
-#pragma unroll
-            for (int c = 0; c < CO; ++c) acc[tp][c] = 0.f;
-        for (int64_t m = ms; m < me; ++m) {
-            const int ow = (int)(m % g.OW), oh = (int)((m / g.OW) % g.OH), b = (int)(m / ((int64_t)g.OW * g.OH));
-            float d[CO];
-#pragma unroll
-            for (int c = 0; c < CO; ++c) d[c] = __bfloat162float(dy[m * CO + c]);
-#pragma unroll
-            for (int tp = 0; tp < TAPS; ++tp) {
-                const int ih = oh * g.stride - g.pt + tp / g.KW, iw = ow * g.stride - g.pl + tp % g.KW;
-                if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) continue;
-                const float xv = __bfloat162float(x[(((int64_t)b * g.H + ih) * g.W + iw) * g.Cin + ci]);
-#pragma unroll
-                for (int c = 0; c < CO; ++c) acc[tp][c] += d[c] * xv;
-            }
-        }
-#pragma unroll
-        for (int tp = 0; tp < TAPS; ++tp)
-#pragma unroll
-            for (int c = 0; c < CO; ++c) atomicAdd(&dw[((int64_t)c * g.Cin + ci) * TAPS + tp], acc[tp][c]);
-    }
-}
-
 DMVAE_API int dmvae_conv_direct_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int OH,
                                       int OW, int Cout, int KH, int KW, int stride, int pad_top, int pad_left,
                                       void* stream) {
@@ -565,15 +531,6 @@ DMVAE_API int dmvae_conv_direct_wgrad(const void* x, const void* dy, float* dw, 
             conv_thin_wgrad_kernel<3, false><<<blocks, 256, smem, st>>>((const bf16*)dy, (const bf16*)x, dw, B, H, W, Cout, rpb);
         }
         DMVAE_CHECK_LAUNCH("conv_thin_wgrad_kernel");
-        return DMVAE_OK;
-    }
-    if (Cout <= 4 && taps == 9 && Cout == 3) {
-        int64_t blocks = 148 * 8;
-        int64_t mpb = ceil_div64(M, blocks);
-        if (mpb < 32) mpb = 32;
-        blocks = ceil_div64(M, mpb);
-        conv_small_cout_wgrad_kernel<3, 9><<<(unsigned)blocks, 128, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, g, mpb);
-        DMVAE_CHECK_LAUNCH("conv_small_cout_wgrad_kernel");
         return DMVAE_OK;
     }
     const bool vec = (Cin % 8 == 0) && (Cout % 8 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)dy & 15) == 0);
