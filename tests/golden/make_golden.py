@@ -171,6 +171,36 @@ def main():
         (dz,) = torch.autograd.grad(loss, zz)
         _, xt, _ = RP.ICPlan().plan(t, x0, z)
         cases[tag] = dict(z=z, x0=x0, t=t, xt=xt, cfg=cfg, loss=loss.detach(), dz=dz, gnorm=log["dmd_gradient_norm"], **outs)
+    # --- config 1 (toy_example_2d/dmd.py): the "dmd" branch of DMDLossFunction.compute_distribution_matching_loss
+    # (:320-360: no CFG, no |p_real| normaliser), learnable points (1536, 2) from create_learnable_points (:139-145)
+    tsrc = open(f"{REF}/toy_example_2d/dmd.py").read()
+    m = re.search(r"    def compute_distribution_matching_loss\(self.*?\n(?=        elif loss_type == \"score_teacher\")", tsrc, re.S)
+    toy_src = textwrap.dedent(m.group(0)) + "    return loss, grad\n"
+    ns2 = {"torch": torch, "expand_t_like_x": lambda t, x: t.view(t.size(0), *([1] * (x.dim() - 1)))}
+    exec(toy_src, ns2)
+    toy_fn = ns2["compute_distribution_matching_loss"]
+    torch.manual_seed(42)
+    points = torch.rand(1536, 2) * 3.0 - 1.5
+    gg = torch.Generator().manual_seed(21)
+    t = torch.rand(1536, generator=gg)
+    x0 = torch.randn(1536, 2, 1, 1, generator=gg)
+    vT = torch.randn(1536, 2, 1, 1, generator=gg)
+    vS = torch.randn(1536, 2, 1, 1, generator=gg)
+
+    class ToyArgs:
+        t0, t1, dmd_loss_type = 0.0, 1.0, "dmd"
+
+    class Self2:
+        pass
+    s2 = Self2()
+    s2.args = ToyArgs()
+    s2.transport = types.SimpleNamespace(sample=lambda x1: (t, x0, x1), path_sampler=RP.ICPlan())
+    s2.base_model = lambda xt, tt, y: vT
+    s2.sit_wo_ddp = lambda xt, tt, y: vS
+    pts = points.clone().requires_grad_(True)
+    loss, grad = toy_fn(s2, pts, torch.zeros(1536, dtype=torch.long))
+    (dpts,) = torch.autograd.grad(loss, pts)
+    cases["toy_fp32"] = dict(points=points, x0=x0, t=t, vT=vT, vS=vS, loss=loss.detach(), dpoints=dpts, grad=grad.detach())
     torch.save(cases, os.path.join(OUT, "dmd.pt"))
     for f in ("flux_ae.pt", "lpips.pt", "dmd.pt"):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -110,6 +110,16 @@ def test_dmd(tag, tol):
     assert rel(dz, c["dz"].float()) <= tol
 
 
+def test_toy_2d_dmd_config():
+    """BASELINE configs[0]: toy_example_2d/dmd.py "dmd" branch (no CFG, no normaliser) on the (1536, 2) learnable points."""
+    c = torch.load(os.path.join(G, "dmd.pt"), weights_only=True)["toy_fp32"]
+    z = c["points"].view(1536, 2, 1, 1)
+    xt = O.dmd_mix_xt(z, c["x0"], c["t"])
+    loss, gnorm, dz = O.dmd_loss(z, xt, c["t"], c["vT"], c["vS"], None, None, 1.0, normalize=False)
+    assert abs(loss.item() - c["loss"].item()) <= 1e-6 * abs(c["loss"].item())
+    assert rel(dz.view(1536, 2), c["dpoints"]) < 1e-6
+
+
 def test_latents_to_spatial_bit_exact():
     x = torch.randn(2, 16, 5)
     y = O.latents_to_spatial(x)
