@@ -1,0 +1,69 @@
+"""Fused optimizer step on flat arenas: global-norm clip + AdamW + EMA in two kernels.
+
+Replaces, for the trainable VAE parameters, the reference's per-step sequence
+    clip_grad_norm_(params, 1.0); optimizer.step(); update_ema(ema_model, model)
+(train_tokenizer.py:415-417,437 with update_ema :140-150; train_dmd.py:540-544).  Parameters, gradients, both Adam moments
+and the EMA copy each live in one flat fp32 buffer; the ``nn.Parameter``s stay ordinary parameters whose ``.data`` / ``.grad``
+are views into those buffers, so ``state_dict()``, ``load_state_dict()`` (in-place copy), DDP-free all-reduce (GradArena)
+and the packed-weight caches (version counters are bumped after every step) keep working.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+from torch import nn
+
+from ._lib import call, ptr
+from .train_arena import GradArena
+
+
+class FlatAdamWEMA:
+    def __init__(self, params: Iterable[nn.Parameter], lr: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
+                 weight_decay: float = 0.0, max_norm: float = 1.0, ema_decay: Optional[float] = 0.9999,
+                 arena: Optional[GradArena] = None):
+        self.arena = arena if arena is not None else GradArena(params)
+        self.params: List[nn.Parameter] = self.arena.params
+        if not self.params or not self.params[0].is_cuda:
+            raise RuntimeError("FlatAdamWEMA needs CUDA parameters (dmvae_b200 has no CPU path)")
+        n = self.arena.flat.numel()
+        dev = self.arena.flat.device
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:                       # move every parameter's storage into the flat buffer
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                off += p.numel()
+        self.m = torch.zeros_like(self.flat_p)
+        self.v = torch.zeros_like(self.flat_p)
+        self.ema = self.flat_p.clone() if ema_decay is not None else None
+        self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.ema_decay = 0.0 if ema_decay is None else ema_decay
+        self.t = 0
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    @torch.no_grad()
+    def step(self, lr: Optional[float] = None) -> torch.Tensor:
+        """One optimizer step on the gradients currently in the arena.  Returns the pre-clip gradient norm (0-d, device)."""
+        self.t += 1
+        n = self.flat_p.numel()
+        self._sumsq.zero_()
+        call("dmvae_grad_sumsq", ptr(self.arena.flat), ptr(self._sumsq), n)
+        call("dmvae_adamw_ema_step", ptr(self.flat_p), ptr(self.arena.flat), ptr(self.m), ptr(self.v), ptr(self.ema),
+             ptr(self._sumsq), ptr(self._norm), n, float(self.lr if lr is None else lr), float(self.betas[0]),
+             float(self.betas[1]), float(self.eps), float(self.wd), int(self.t), float(self.max_norm), float(self.ema_decay))
+        torch.autograd.graph.increment_version(self.params)      # the kernel wrote through raw pointers
+        return self._norm[0]
+
+    def ema_state(self, named_params: Dict[str, nn.Parameter]) -> Dict[str, torch.Tensor]:
+        """EMA tensors keyed like ``named_parameters()`` (the trainable part of the reference's ``vae_ema`` checkpoint entry)."""
+        out, off = {}, 0
+        by_id = {id(p): k for k, p in named_params.items()}
+        for p in self.params:
+            if id(p) in by_id and self.ema is not None:
+                out[by_id[id(p)]] = self.ema[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        return out

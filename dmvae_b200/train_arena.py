@@ -1,0 +1,87 @@
+"""Flat gradient arena + data-parallel exchange (row A7): the DDP gradient all-reduce of train_dmd.py:348 /
+train_tokenizer.py:302 as chunked NCCL all-reduces over one contiguous fp32 buffer."""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Tuple
+
+import torch
+import torch.distributed as tdist
+from torch import nn
+
+
+class GradArena:
+    """All trainable gradients as views of one flat fp32 buffer, exchanged with one NCCL all-reduce per chunk over
+    NVLink/NVSwitch instead of DDP's 25 MB buckets.  With ``overlap=True`` a chunk's all-reduce is issued from an
+    autograd hook as soon as every gradient inside it has been accumulated (backward runs output-to-input, so the
+    tail of the arena completes first), i.e. the exchange overlaps the rest of the backward pass like DDP's bucketed
+    reduction (train_dmd.py:348).  With world_size == 1 it is just a flat buffer."""
+
+    def __init__(self, params: Iterable[nn.Parameter], chunks: int = 4, overlap: bool = True):
+        self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.chunks = max(1, min(chunks, len(self.params) or 1))
+        # chunk boundaries on parameter boundaries, roughly equal in bytes
+        target = (n + self.chunks - 1) // self.chunks
+        self.bounds: List[Tuple[int, int]] = []          # [start, end) element ranges
+        self.chunk_of: Dict[int, int] = {}
+        start, off = 0, 0
+        for i, p in enumerate(self.params):
+            self.chunk_of[id(p)] = len(self.bounds)
+            off += p.numel()
+            if off - start >= target or i == len(self.params) - 1:
+                self.bounds.append((start, off))
+                start = off
+        self.members = [sum(1 for p in self.params if self.chunk_of[id(p)] == c) for c in range(len(self.bounds))]
+        self._pending = list(self.members)
+        self._handles: List = []
+        self._launched = [False] * len(self.bounds)
+        self._attach()
+        self.overlap = overlap and self._distributed()
+        if self.overlap:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._on_grad_ready)
+
+    @staticmethod
+    def _distributed() -> bool:
+        return tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
+
+    def _attach(self):
+        off = 0
+        for p in self.params:      # (re-)attach in case an optimizer dropped the views (set_to_none)
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+        self._attach()
+        self._pending = list(self.members)
+        self._launched = [False] * len(self.bounds)
+        self._handles = []
+
+    def _launch(self, c: int):
+        s, e = self.bounds[c]
+        self._launched[c] = True
+        self._handles.append(tdist.all_reduce(self.flat[s:e], op=tdist.ReduceOp.SUM, async_op=True))
+
+    def _on_grad_ready(self, p: nn.Parameter):
+        c = self.chunk_of[id(p)]
+        self._pending[c] -= 1
+        if self._pending[c] == 0 and not self._launched[c]:
+            self._launch(c)
+
+    def allreduce(self):
+        """Finish the exchange: launch whatever was not launched from hooks, wait, average."""
+        if not self._distributed():
+            return
+        for c in range(len(self.bounds)):
+            if not self._launched[c]:
+                self._launch(c)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        self.flat.div_(tdist.get_world_size())
+
+

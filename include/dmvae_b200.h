@@ -162,6 +162,14 @@ int dmvae_nhwc_to_nchw(const void* src, void* dst, int64_t B, int C, int64_t HW,
 /* out = a + b (bf16, fp32 add, one rounding): gradient fan-in of the residual branches (:52, :82). */
 int dmvae_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------ N2: fused optimizer step ---------------- */
+/* Replaces clip_grad_norm_ + AdamW.step + update_ema (train_tokenizer.py:140-150,415-417,437; train_dmd.py:540-544) on
+ * flat fp32 arenas: sumsq[0] += sum g^2 ; then g *= min(1, max_norm/(||g||+1e-6)), AdamW (torch semantics), EMA. */
+int dmvae_grad_sumsq(const float* g, double* sumsq, int64_t n, void* stream);
+int dmvae_adamw_ema_step(float* p, float* g, float* m, float* v, float* ema, const double* sumsq, float* norm_out,
+                         int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                         float max_norm, float ema_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -325,3 +325,33 @@ def test_c_abi_error_behaviour():
     blk = ResnetBlock(32, 64).to(DEV)
     out = blk(torch.randn(1, 32, 7, 9, device=DEV))
     assert out.shape == (1, 64, 7, 9) and torch.isfinite(out.float()).all()
+
+
+def test_fused_clip_adamw_ema_matches_torch():
+    """N2: dmvae_grad_sumsq + dmvae_adamw_ema_step on flat arenas vs clip_grad_norm_ + torch.optim.AdamW + update_ema
+    (train_tokenizer.py:140-150,415-417,437).  fp32 elementwise math in a different op order: 1e-6."""
+    from dmvae_b200.optim import FlatAdamWEMA
+    torch.manual_seed(0)
+    net_a = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.GELU(), torch.nn.Linear(64, 19)).to(DEV)
+    net_b = copy.deepcopy(net_a)
+    opt_b = torch.optim.AdamW(net_b.parameters(), lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.01)
+    ema_b = [p.detach().clone() for p in net_b.parameters()]
+    opt_a = FlatAdamWEMA(net_a.parameters(), lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.01, max_norm=0.5, ema_decay=0.99)
+    for it in range(5):
+        x = torch.randn(8, 37, device=DEV) * (3.0 if it % 2 else 0.3)        # some steps clip, some do not
+        opt_a.arena.zero()
+        net_a(x).square().mean().backward()
+        norm_a = opt_a.step()
+        opt_b.zero_grad(set_to_none=True)
+        net_b(x).square().mean().backward()
+        norm_b = torch.nn.utils.clip_grad_norm_(net_b.parameters(), 0.5)
+        opt_b.step()
+        for e, p in zip(ema_b, net_b.parameters()):
+            e.mul_(0.99).add_(p.data, alpha=0.01)
+        assert abs(norm_a.item() - norm_b.item()) < 1e-5 * norm_b.item()
+        for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+            assert rel(pa.data, pb.data) < 2e-6
+    ema_a = opt_a.ema_state(dict(net_a.named_parameters()))
+    for (k, ea), eb in zip(ema_a.items(), ema_b):
+        assert rel(ea, eb) < 2e-6, k
+    assert set(net_a.state_dict().keys()) == set(net_b.state_dict().keys())
