@@ -198,49 +198,69 @@ DMVAE_API int dmvae_add_bf16(const void* a, const void* b, void* out, int64_t n,
 // ---- weight packing ------------------------------------------------------------------------------------------
 // w[co][ci][kh][kw] fp32  ->  wf[tap][co][ci] bf16  (forward operand, K = ci contiguous)
 //                         ->  wd[tap'][ci][co] bf16 (dgrad operand: tap' = flipped tap, K = co contiguous)
+// One CTA owns a 32(co) x 32(ci) tile for all taps: coalesced fp32 reads, shared-memory transpose, 64-byte bf16 segments
+// out in both layouts.  Runs once per optimizer step per conv (the packed operands are a cache of the fp32 parameter).
+#define PK_T 32
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wf,
-                                                           bf16* __restrict__ wd, int Cout, int Cin, int KH, int KW) {
-    const int64_t n = (int64_t)Cout * Cin * KH * KW;
-    const int taps = KH * KW;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        // i enumerates the *packed forward* layout so writes to wf are coalesced
-        const int ci = (int)(i % Cin);
-        const int co = (int)((i / Cin) % Cout);
-        const int tap = (int)(i / ((int64_t)Cin * Cout));
-        const float v = w[((int64_t)co * Cin + ci) * taps + tap];
-        const bf16 h = __float2bfloat16_rn(v);
-        if (wf) wf[i] = h;
-        if (wd) wd[((int64_t)(taps - 1 - tap) * Cin + ci) * Cout + co] = h;
+                                                           bf16* __restrict__ wd, int Cout, int Cin, int taps) {
+    extern __shared__ float tile[];                    // [PK_T co][PK_T ci * taps + 1]
+    const int co0 = blockIdx.x * PK_T, ci0 = blockIdx.y * PK_T;
+    const int row = PK_T * taps + 1;
+    const int nci = min(PK_T, Cin - ci0), nco = min(PK_T, Cout - co0);
+    // load: for each co, the (ci0 .. ci0+nci) x taps block is contiguous in w
+    for (int i = threadIdx.x; i < nco * nci * taps; i += blockDim.x) {
+        const int c = i / (nci * taps), r = i - c * (nci * taps);
+        tile[c * row + r] = w[((int64_t)(co0 + c) * Cin + ci0) * taps + r];
     }
+    __syncthreads();
+    // wf[tap][co][ci]: consecutive threads -> consecutive ci
+    if (wf)
+        for (int i = threadIdx.x; i < taps * nco * nci; i += blockDim.x) {
+            const int ci = i % nci, c = (i / nci) % nco, tap = i / (nci * nco);
+            wf[((int64_t)tap * Cout + co0 + c) * Cin + ci0 + ci] = __float2bfloat16_rn(tile[c * row + ci * taps + tap]);
+        }
+    // wd[taps-1-tap][ci][co]: consecutive threads -> consecutive co
+    if (wd)
+        for (int i = threadIdx.x; i < taps * nci * nco; i += blockDim.x) {
+            const int c = i % nco, ci = (i / nco) % nci, tap = i / (nco * nci);
+            wd[((int64_t)(taps - 1 - tap) * Cin + ci0 + ci) * Cout + co0 + c] = __float2bfloat16_rn(tile[c * row + ci * taps + tap]);
+        }
 }
 
 DMVAE_API int dmvae_pack_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KH, int KW, void* stream) {
     DMVAE_CHECK_ARG(w && (w_fwd || w_dgrad), "pack_weights: null pointer");
     DMVAE_CHECK_ARG(Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "pack_weights: bad shape");
-    const int64_t n = (int64_t)Cout * Cin * KH * KW;
-    pack_weights_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)w_fwd, (bf16*)w_dgrad, Cout, Cin, KH, KW);
+    const int taps = KH * KW;
+    const size_t smem = (size_t)PK_T * (PK_T * taps + 1) * sizeof(float);
+    DMVAE_CHECK_ARG(smem <= 96 * 1024, "pack_weights: filter too large (%d taps)", taps);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(pack_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    dim3 grid((unsigned)((Cout + PK_T - 1) / PK_T), (unsigned)((Cin + PK_T - 1) / PK_T));
+    pack_weights_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w, (bf16*)w_fwd, (bf16*)w_dgrad, Cout, Cin, taps);
     DMVAE_CHECK_LAUNCH("pack_weights_kernel");
     return DMVAE_OK;
 }
 
-// tap-major wgrad scratch [tap][Cout][Cin] -> state_dict layout dw[co][ci][tap] (accumulate=1: +=)
+// tap-major wgrad scratch [tap][Cout][Cin] -> state_dict layout dw[co][ci][tap] (accumulate=1: +=).
+// One CTA per (co, 256-wide ci chunk): taps coalesced row reads, shared-memory interleave, one contiguous write.
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restrict__ dwp, float* __restrict__ dw,
                                                            int Cout, int Cin, int taps, int accumulate) {
-    const int64_t n = (int64_t)Cout * Cin * taps;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        // i enumerates the destination so the writes are coalesced; reads of a 3x3 filter hit 9 planes
-        const int tap = (int)(i % taps);
-        const int64_t cc = i / taps;                       // co*Cin + ci
-        const float v = dwp[(int64_t)tap * Cout * Cin + cc];
-        dw[i] = accumulate ? dw[i] + v : v;
-    }
+    extern __shared__ float s_t[];                     // [256 ci][taps] interleaved as the destination wants it
+    const int co = blockIdx.x, ci0 = blockIdx.y * 256;
+    const int nci = min(256, Cin - ci0);
+    for (int tap = 0; tap < taps; ++tap)
+        if (threadIdx.x < nci)
+            s_t[threadIdx.x * taps + tap] = dwp[((int64_t)tap * Cout + co) * Cin + ci0 + threadIdx.x];
+    __syncthreads();
+    float* dst = dw + ((int64_t)co * Cin + ci0) * taps;
+    for (int i = threadIdx.x; i < nci * taps; i += blockDim.x) dst[i] = accumulate ? dst[i] + s_t[i] : s_t[i];
 }
 
 DMVAE_API int dmvae_wgrad_unpack(const float* dw_tap_major, float* dw, int Cout, int Cin, int taps, int accumulate, void* stream) {
     DMVAE_CHECK_ARG(dw_tap_major && dw, "wgrad_unpack: null pointer");
-    DMVAE_CHECK_ARG(Cout > 0 && Cin > 0 && taps > 0, "wgrad_unpack: bad shape");
-    const int64_t n = (int64_t)Cout * Cin * taps;
-    wgrad_unpack_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dw_tap_major, dw, Cout, Cin, taps, accumulate);
+    DMVAE_CHECK_ARG(Cout > 0 && Cin > 0 && taps > 0 && taps <= 32, "wgrad_unpack: bad shape");
+    dim3 grid((unsigned)Cout, (unsigned)((Cin + 255) / 256));
+    wgrad_unpack_kernel<<<grid, 256, (size_t)256 * taps * sizeof(float), (cudaStream_t)stream>>>(dw_tap_major, dw, Cout, Cin, taps, accumulate);
     DMVAE_CHECK_LAUNCH("wgrad_unpack_kernel");
     return DMVAE_OK;
 }
