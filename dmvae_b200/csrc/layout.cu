@@ -207,24 +207,24 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
     const int co0 = blockIdx.x * PK_T, ci0 = blockIdx.y * PK_T;
     const int row = PK_T * taps + 1;
     const int nci = min(PK_T, Cin - ci0), nco = min(PK_T, Cout - co0);
+    // 32 x 8 thread layout, no integer division in the loops
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     // load: for each co, the (ci0 .. ci0+nci) x taps block is contiguous in w
-    for (int i = threadIdx.x; i < nco * nci * taps; i += blockDim.x) {
-        const int c = i / (nci * taps), r = i - c * (nci * taps);
-        tile[c * row + r] = w[((int64_t)(co0 + c) * Cin + ci0) * taps + r];
+    for (int c = ty; c < nco; c += 8) {
+        const float* src = w + ((int64_t)(co0 + c) * Cin + ci0) * taps;
+        for (int r = tx; r < nci * taps; r += 32) tile[c * row + r] = src[r];
     }
     __syncthreads();
-    // wf[tap][co][ci]: consecutive threads -> consecutive ci
-    if (wf)
-        for (int i = threadIdx.x; i < taps * nco * nci; i += blockDim.x) {
-            const int ci = i % nci, c = (i / nci) % nco, tap = i / (nci * nco);
-            wf[((int64_t)tap * Cout + co0 + c) * Cin + ci0 + ci] = __float2bfloat16_rn(tile[c * row + ci * taps + tap]);
-        }
-    // wd[taps-1-tap][ci][co]: consecutive threads -> consecutive co
-    if (wd)
-        for (int i = threadIdx.x; i < taps * nci * nco; i += blockDim.x) {
-            const int c = i % nco, ci = (i / nco) % nci, tap = i / (nco * nci);
-            wd[((int64_t)(taps - 1 - tap) * Cin + ci0 + ci) * Cout + co0 + c] = __float2bfloat16_rn(tile[c * row + ci * taps + tap]);
-        }
+    // wf[tap][co][ci]: a warp writes 32 consecutive ci
+    if (wf && tx < nci)
+        for (int tap = 0; tap < taps; ++tap)
+            for (int c = ty; c < nco; c += 8)
+                wf[((int64_t)tap * Cout + co0 + c) * Cin + ci0 + tx] = __float2bfloat16_rn(tile[c * row + tx * taps + tap]);
+    // wd[taps-1-tap][ci][co]: a warp writes 32 consecutive co
+    if (wd && tx < nco)
+        for (int tap = 0; tap < taps; ++tap)
+            for (int ci = ty; ci < nci; ci += 8)
+                wd[((int64_t)(taps - 1 - tap) * Cin + ci0 + ci) * Cout + co0 + tx] = __float2bfloat16_rn(tile[tx * row + ci * taps + tap]);
 }
 
 DMVAE_API int dmvae_pack_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KH, int KW, void* stream) {
