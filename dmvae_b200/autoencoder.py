@@ -19,12 +19,6 @@ from torch import Tensor, nn
 from . import ops
 
 
-import os as _os
-
-# Batch-slice threshold for the high-resolution decoder levels (bytes per activation tensor); 0 disables slicing.
-L2_SLICE_BYTES = int(_os.environ.get("DMVAE_L2_SLICE_BYTES", "0"))
-
-
 def _to_cl(x: Tensor) -> Tensor:
     """NCHW-logical tensor -> contiguous (B, H, W, C) bf16 (zero-copy when already channels-last bf16)."""
     if x.dtype == torch.bfloat16:
@@ -270,43 +264,15 @@ class Decoder(_PackMixin, nn.Module):
         h = self.mid.block_1._forward_cl(h)
         h = self.mid.attn_1._forward_cl(h)
         h = self.mid.block_2._forward_cl(h)
-        # Every op below is per-image (convs, per-sample GroupNorm), so the batch may be walked in slices once the
-        # activations outgrow the L2: a slice's tensors (<= L2_SLICE_BYTES each) are then produced and consumed out of the
-        # 126 MB L2 instead of HBM, in the forward pass and -- because autograd replays slices one after another -- in
-        # the backward pass too.  Numerically identical to the unsliced walk.
-        levels = list(reversed(range(self.num_resolutions)))
-        pos = 0
-        while pos < len(levels):
-            B, H, W, c = h.shape
-            nxt = self.up[levels[pos]].block[0].out_channels
-            scale = 4 if levels[pos] != 0 else 1
-            if B > 1 and L2_SLICE_BYTES > 0 and B * H * W * max(c, nxt) * 2 * scale > L2_SLICE_BYTES:
-                break
-            h = self._run_level(levels[pos], h)
-            pos += 1
-        if pos == len(levels):
-            return ops.to_nchw(self._tail(h), out_dtype)
-        per_image = h.shape[1] * h.shape[2] * max(h.shape[3], self.up[levels[pos]].block[0].out_channels) * 2 * 4
-        step = max(1, min(h.shape[0], L2_SLICE_BYTES // max(per_image, 1)))
-        outs = []
-        for b0 in range(0, h.shape[0], step):
-            hs = h[b0:b0 + step]
-            for lvl in levels[pos:]:
-                hs = self._run_level(lvl, hs)
-            outs.append(self._tail(hs))
-        return ops.to_nchw(torch.cat(outs, dim=0), out_dtype)
-
-    def _run_level(self, i_level: int, h: Tensor) -> Tensor:
-        for i_block in range(self.num_res_blocks + 1):
-            h = self.up[i_level].block[i_block]._forward_cl(h)
-            if len(self.up[i_level].attn) > 0:
-                h = self.up[i_level].attn[i_block]._forward_cl(h)
-        if i_level != 0:
-            h = self.up[i_level].upsample._forward_cl(h)
-        return h
-
-    def _tail(self, h: Tensor) -> Tensor:
-        return _conv(self, "conv_out", self.conv_out, _gn(self.norm_out, h, True))
+        for i_level in reversed(range(self.num_resolutions)):
+            for i_block in range(self.num_res_blocks + 1):
+                h = self.up[i_level].block[i_block]._forward_cl(h)
+                if len(self.up[i_level].attn) > 0:
+                    h = self.up[i_level].attn[i_block]._forward_cl(h)
+            if i_level != 0:
+                h = self.up[i_level].upsample._forward_cl(h)
+        h = _conv(self, "conv_out", self.conv_out, _gn(self.norm_out, h, True))
+        return ops.to_nchw(h, out_dtype)
 
     def post_init(self, z_channels):
         """Swap the stem for nearest-2x + 3x3 followed by the 3x3 widening conv (reference :271-275)."""
