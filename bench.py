@@ -201,14 +201,19 @@ def run_ours(args):
     _lib.Stats.reset()
     _lib.Stats.work_fn = _work
     _lib.Stats.timing = True
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
     tr.step(resident[0])
+    pe1.record()
     torch.cuda.synchronize()
     _lib.Stats.timing = False
+    prof_total_ms = pe0.elapsed_time(pe1)
     per = {}
     for name, a, b, work in _lib.Stats.events:
         d = per.setdefault(name, [0, 0.0, 0.0])
         d[0] += 1; d[1] += a.elapsed_time(b); d[2] += work
-    step_ms_prof = sum(v[1] for v in per.values())
+    step_ms_prof = prof_total_ms          # whole profiled step on the device (library kernels + the PyTorch ones)
+    lib_ms = sum(v[1] for v in per.values())
 
     if rank != 0:
         if world > 1:
@@ -238,7 +243,9 @@ def run_ours(args):
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": B * 3 * 256 * 256 * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last.get("loss")},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-        "wgrad": {"achieved_tflops": round(wg[2] / (wg[1] * 1e-3) / 1e12, 1) if wg[1] else None, "launches_per_step": wg[0]},
+        "wgrad": {"achieved_tflops": round(wg[2] / (wg[1] * 1e-3) / 1e12, 1) if wg[1] else None, "launches_per_step": wg[0],
+                  "share_of_step": round(wg[1] / max(step_ms_prof, 1e-9), 4)},
+        "profiled_step_ms": {"total": round(prof_total_ms, 3), "library_kernels": round(lib_ms, 3)},
         "kernels_ms_per_step": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -25,10 +25,21 @@ static int gn_geom(int C, GnGeom* g, const char* who) {
     return DMVAE_OK;
 }
 
+#include <stdlib.h>
+static int gn_ctas_per_sm() {          // tuning knob (DMVAE_GN_CTAS_PER_SM), default 16 CTAs per SM worth of grid
+    static int v = 0;
+    if (!v) { const char* e = getenv("DMVAE_GN_CTAS_PER_SM"); v = e ? atoi(e) : 16; if (v < 1) v = 16; }
+    return v;
+}
+static int gn_min_passes() {           // minimum row-passes of work per CTA (amortises the per-CTA coefficient prologue)
+    static int v = 0;
+    if (!v) { const char* e = getenv("DMVAE_GN_MIN_PASSES"); v = e ? atoi(e) : 16; if (v < 1) v = 16; }
+    return v;
+}
 static void gn_grid(int64_t B, int64_t HW, int rows, dim3* grid, int64_t* ppb) {
-    // aim for >= 4 waves of 148 SMs x 2 CTAs, but at least 4 passes of work per CTA
-    int64_t chunks = (148 * 16 + B - 1) / B;
-    int64_t max_chunks = ceil_div64(HW, (int64_t)rows * 8);
+    // aim for several waves of CTAs, but at least 8 row-passes of work per CTA
+    int64_t chunks = (148 * gn_ctas_per_sm() + B - 1) / B;
+    int64_t max_chunks = ceil_div64(HW, (int64_t)rows * gn_min_passes());
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     *ppb = ceil_div64(HW, chunks);
