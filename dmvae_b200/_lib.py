@@ -37,6 +37,10 @@ SIGNATURES = {
     "dmvae_conv_tc_supported": [_i] * 7,
     "dmvae_conv_tc_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "dmvae_conv_tc_set_tile_mode": [_i],
+    "dmvae_conv_tc_strided_supported": [_i] * 10,
+    "dmvae_conv_tc_fwd_strided": [_p, _p, _p, _p] + [_i] * 12 + [_p],
+    "dmvae_conv_tc_wgrad_strided": [_p, _p, _p] + [_i] * 12 + [_p],
+    "dmvae_zero_insert2x": [_p, _p, _i64, _i, _i, _i, _p],
     "dmvae_conv_tc_wgrad_supported": [_i] * 7,
     "dmvae_conv_tc_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "dmvae_wgrad_unpack": [_p, _p, _i, _i, _i, _i, _p],

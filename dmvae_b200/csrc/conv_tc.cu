@@ -182,7 +182,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int n, i
 }
 
 struct TcGeom {
-    int B, H, W, Cin, Cout, KH, KW, pt, pl;
+    int B, H, W, Cin, Cout, KH, KW, pt, pl;      // H, W: OUTPUT image size (tiles live on the output grid)
+    int stride, IH, IW;                          // conv stride and INPUT image size (IH = H, IW = W when stride == 1)
     int cpg;               // Cout / 32 (GroupNorm group width) when output statistics are requested
     int BW, BH;            // pixel tile = BH rows x BW cols of one image (BH*BW = 128)
     int tiles_w, tiles_h;  // W/BW, H/BH
@@ -243,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
                 const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
-                const int w0 = tw * g.BW - g.pl, h0 = th * g.BH - g.pt, n0 = nt * BN;
+                const int w0 = tw * g.BW * g.stride - g.pl, h0 = th * g.BH * g.stride - g.pt, n0 = nt * BN;
                 for (int tap = 0; tap < g.KH * g.KW; ++tap) {
                     const int kh = tap / g.KW, kw = tap % g.KW;
                     for (int kc = 0; kc < g.k_chunks; ++kc) {
@@ -438,7 +439,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
                 const int mt = 2 * (pt / g.n_tiles) + (int)rank, nt = pt % g.n_tiles;
                 const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
-                const int w0 = tw * g.BW - g.pl, h0 = th * g.BH - g.pt, n0 = nt * BN + (int)rank * (BN / 2);
+                const int w0 = tw * g.BW * g.stride - g.pl, h0 = th * g.BH * g.stride - g.pt, n0 = nt * BN + (int)rank * (BN / 2);
                 for (int tap = 0; tap < g.KH * g.KW; ++tap) {
                     const int kh = tap / g.KW, kw = tap % g.KW;
                     for (int kc = 0; kc < g.k_chunks; ++kc) {
@@ -544,7 +545,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 struct WgGeom {
-    int B, H, W, Cin, Cout, KH, KW, pt, pl;
+    int B, H, W, Cin, Cout, KH, KW, pt, pl;      // H, W: dy (output) image size
+    int stride, IH, IW;                          // conv stride and x (input) image size
     int BW, BH, tiles_w, tiles_h;
     int pix_tiles;          // B * tiles_h * tiles_w
     int co_tiles, ci_tiles, tap_groups, splits, tiles_per_split;
@@ -624,7 +626,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
 #pragma unroll
                     for (int j = 0; j < BN / 64; ++j)
                         tma_load_4d(sb + tp * C::B_BYTES_TAP + j * WG_BOX_BYTES, &map_x, &full[stage], ci0 + j * 64,
-                                    w0 + kw - g.pl, h0 + kh - g.pt, b);
+                                    w0 * g.stride + kw - g.pl, h0 * g.stride + kh - g.pt, b);
                 }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -724,12 +726,14 @@ std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
 // bf16 tensor, rank 3 or 4, innermost dim contiguous, 128B swizzle, zero OOB fill
-int get_tensor_map(const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, CUtensorMap* out) {
+// `box` counts elements landing in shared memory per dimension; `estr` (optional) is the traversal stride per dimension
+// (a stride-2 conv samples every other pixel: the TMA unit does the subsampling).
+int get_tensor_map(const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, CUtensorMap* out, const uint32_t* estr = nullptr) {
     MapKey key;
     memset(&key, 0, sizeof(key));
     key.v[0] = (uint64_t)(uintptr_t)ptr;
     key.v[1] = (uint64_t)rank;
-    for (int i = 0; i < rank; ++i) key.v[2 + i] = dims[i] | ((uint64_t)box[i] << 40);
+    for (int i = 0; i < rank; ++i) key.v[2 + i] = dims[i] | ((uint64_t)box[i] << 40) | ((uint64_t)(estr ? estr[i] : 1) << 56);
     {
         std::lock_guard<std::mutex> lk(g_map_mu);
         auto itc = g_map_cache.find(key);
@@ -740,7 +744,8 @@ int get_tensor_map(const void* ptr, int rank, const uint64_t* dims, const uint32
     cuuint64_t gdim[4]; cuuint64_t gstride[3]; cuuint32_t bdim[4]; cuuint32_t estride[4];
     uint64_t stride = 2;
     for (int i = 0; i < rank; ++i) {
-        gdim[i] = dims[i]; bdim[i] = box[i]; estride[i] = 1;
+        estride[i] = estr ? estr[i] : 1;
+        gdim[i] = dims[i]; bdim[i] = box[i] * estride[i];
         stride *= dims[i];
         if (i < rank - 1) gstride[i] = stride;
     }
@@ -779,9 +784,10 @@ template <int BN, int MT>
 int launch_conv_tc(const void* x, const void* w, const float* bias, const void* res, void* y, double* stats, TcGeom g, cudaStream_t st) {
     using C = Cfg<BN, MT>;
     CUtensorMap ma, mb;
-    const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
     const uint32_t abox[4] = {BK, (uint32_t)g.BW, (uint32_t)g.BH, 1};
-    int rc = get_tensor_map(x, 4, adims, abox, &ma);
+    const uint32_t astr[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
+    int rc = get_tensor_map(x, 4, adims, abox, &ma, astr);
     if (rc) return rc;
     const uint64_t bdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, (uint64_t)(g.KH * g.KW)};
     const uint32_t bbox[3] = {BK, BN, 1};
@@ -804,9 +810,10 @@ template <int BN>
 int launch_conv_tc2(const void* x, const void* w, const float* bias, const void* res, void* y, double* stats, TcGeom g, cudaStream_t st) {
     using C = Cfg2<BN>;
     CUtensorMap ma, mb;
-    const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
     const uint32_t abox[4] = {BK, (uint32_t)g.BW, (uint32_t)g.BH, 1};
-    int rc = get_tensor_map(x, 4, adims, abox, &ma);
+    const uint32_t astr[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
+    int rc = get_tensor_map(x, 4, adims, abox, &ma, astr);
     if (rc) return rc;
     const uint64_t bdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, (uint64_t)(g.KH * g.KW)};
     const uint32_t bbox[3] = {BK, BN / 2, 1};
@@ -852,6 +859,7 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     TcGeom g;
     g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
     g.pt = (KH - 1) / 2; g.pl = (KW - 1) / 2;
+    g.stride = 1; g.IH = H; g.IW = W;
     double* stats = nullptr;
     g.cpg = 0;
     if (gn_stats) {
@@ -914,8 +922,9 @@ int launch_wgrad_tc(const void* x, const void* dy, float* dwp, WgGeom g, cudaStr
     const uint64_t ddims[4] = {(uint64_t)g.Cout, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
     int rc = get_tensor_map(dy, 4, ddims, box, &mdy);
     if (rc) return rc;
-    const uint64_t xdims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
-    rc = get_tensor_map(x, 4, xdims, box, &mx);
+    const uint64_t xdims[4] = {(uint64_t)g.Cin, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
+    const uint32_t xstr[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
+    rc = get_tensor_map(x, 4, xdims, box, &mx, xstr);
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
@@ -958,6 +967,7 @@ DMVAE_API int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_m
     WgGeom g;
     g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
     g.pt = (KH - 1) / 2; g.pl = (KW - 1) / 2;
+    g.stride = 1; g.IH = H; g.IW = W;
     pick_pixel_tile64(H, W, &g.BW, &g.BH);
     g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
     g.pix_tiles = B * g.tiles_w * g.tiles_h;
@@ -978,4 +988,62 @@ DMVAE_API int dmvae_conv_tc_set_tile_mode(int mode) {
     if (mode == 5) { g_pair_default = 0; g_force_mt = 0; return DMVAE_OK; }      // heuristic, single-CTA tiles only
     g_force_mt = (mode >= 1 && mode <= 3) ? mode : 0;
     return DMVAE_OK;
+}
+
+// ---------------------------------------------------------------- strided convolution (flux_ae.Downsample, :85-95)
+// Stride-2 3x3 with arbitrary top/left padding: the output grid is tiled as usual and the A operand is fetched with TMA
+// element strides of 2 over the input image (right/bottom zero padding = TMA out-of-bounds fill).
+DMVAE_API int dmvae_conv_tc_strided_supported(int B, int IH, int IW, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride) {
+    int bw, bh;
+    if (stride != 2 || B <= 0 || Cin % 8 != 0 || Cin < 32 || Cout % 8 != 0 || Cout < 32 || KH != 3 || KW != 3) return 0;
+    if (!pick_pixel_tile_n(OH, OW, BM, &bw, &bh)) return 0;
+    return bw * stride <= 256 && bh * stride <= 256;
+}
+
+DMVAE_API int dmvae_conv_tc_fwd_strided(const void* x, const void* w_packed, const float* bias, void* y, int B, int IH, int IW,
+                                        int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad_top, int pad_left,
+                                        void* stream) {
+    DMVAE_CHECK_ARG(x && w_packed && y, "conv_tc_fwd_strided: null pointer");
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0,
+                    "conv_tc_fwd_strided: buffers must be 16-byte aligned");
+    if (!dmvae_conv_tc_strided_supported(B, IH, IW, Cin, OH, OW, Cout, KH, KW, stride))
+        return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_tc_fwd_strided: shape B=%d %dx%d->%dx%d Cin=%d Cout=%d s=%d not supported", B, IH, IW, OH, OW, Cin, Cout, stride);
+    TcGeom g;
+    g.B = B; g.H = OH; g.W = OW; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
+    g.pt = pad_top; g.pl = pad_left; g.stride = stride; g.IH = IH; g.IW = IW; g.cpg = 0;
+    g.k_chunks = (Cin + BK - 1) / BK;
+    pick_pixel_tile_n(OH, OW, BM, &g.BW, &g.BH);
+    g.tiles_w = OW / g.BW; g.tiles_h = OH / g.BH;
+    g.m_tiles = B * g.tiles_w * g.tiles_h;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bn = (Cout % 256 == 0 || Cout > 256) ? 256 : 128;
+    g.n_tiles = (Cout + bn - 1) / bn;
+    if (bn == 256 && Cout % 256 == 0 && g.m_tiles % 2 == 0 && g_force_mt != 1)
+        return launch_conv_tc2<256>(x, w_packed, bias, nullptr, y, nullptr, g, st);
+    return bn == 256 ? launch_conv_tc<256, 1>(x, w_packed, bias, nullptr, y, nullptr, g, st)
+                     : launch_conv_tc<128, 1>(x, w_packed, bias, nullptr, y, nullptr, g, st);
+}
+
+// strided weight gradient: dy lives on the OHxOW grid, x is sampled with TMA element strides
+DMVAE_API int dmvae_conv_tc_wgrad_strided(const void* x, const void* dy, float* dw_tap_major, int B, int IH, int IW, int Cin,
+                                          int OH, int OW, int Cout, int KH, int KW, int stride, int pad_top, int pad_left,
+                                          void* stream) {
+    DMVAE_CHECK_ARG(x && dy && dw_tap_major, "conv_tc_wgrad_strided: null pointer");
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dw_tap_major & 15) == 0,
+                    "conv_tc_wgrad_strided: buffers must be 16-byte aligned");
+    int bw, bh;
+    if (stride != 2 || KH != 3 || KW != 3 || Cin % 8 != 0 || Cout % 8 != 0 || Cin < 32 || Cout < 32 || !pick_pixel_tile64(OH, OW, &bw, &bh) ||
+        bw * stride > 256 || bh * stride > 256)
+        return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_tc_wgrad_strided: shape B=%d %dx%d->%dx%d Cin=%d Cout=%d s=%d not supported", B, IH, IW, OH, OW, Cin, Cout, stride);
+    WgGeom g;
+    g.B = B; g.H = OH; g.W = OW; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
+    g.pt = pad_top; g.pl = pad_left; g.stride = stride; g.IH = IH; g.IW = IW;
+    g.BW = bw; g.BH = bh;
+    g.tiles_w = OW / bw; g.tiles_h = OH / bh;
+    g.pix_tiles = B * g.tiles_w * g.tiles_h;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool wide_m = Cout >= 256 && g_force_mt != 1;
+    if (Cin >= 256) return wide_m ? launch_wgrad_tc<256, 2, 1>(x, dy, dw_tap_major, g, st) : launch_wgrad_tc<256, 1, 1>(x, dy, dw_tap_major, g, st);
+    if (wide_m) return launch_wgrad_tc<128, 2, 2>(x, dy, dw_tap_major, g, st);
+    return launch_wgrad_tc<128, 1, 3>(x, dy, dw_tap_major, g, st);
 }

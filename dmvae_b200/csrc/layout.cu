@@ -310,3 +310,34 @@ DMVAE_API int dmvae_grad_patches(const void* dy, void* patches, int64_t B, int H
     DMVAE_CHECK_LAUNCH("grad_patches_kernel");
     return DMVAE_OK;
 }
+
+// ---- zero insertion for the data gradient of a stride-2 conv (flux_ae.Downsample: pad (0,1,0,1), 3x3, stride 2) ----------
+// dyz[b][2*oh+1][2*ow+1][c] = dy[b][oh][ow][c], zero elsewhere (H = 2*OH, W = 2*OW).  Then
+//   dx = conv3x3_same(dyz, flipped/transposed weights)
+// which runs on the tcgen05 tile (4x the minimal FLOPs of three small layers, instead of a CUDA-core gather).
+__global__ void __launch_bounds__(256) zero_insert2x_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dyz, int64_t B,
+                                                            int OH, int OW, int vc) {
+    const int H = 2 * OH, W = 2 * OW;
+    const int64_t n = B * H * W * vc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vc);
+        int64_t p = i / vc;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int64_t b = p / H;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if ((h & 1) && (w & 1)) val = dy[((b * OH + (h >> 1)) * OW + (w >> 1)) * vc + v];
+        dyz[i] = val;
+    }
+}
+
+DMVAE_API int dmvae_zero_insert2x(const void* dy, void* dyz, int64_t B, int OH, int OW, int C, void* stream) {
+    DMVAE_CHECK_ARG(dy && dyz, "zero_insert2x: null pointer");
+    DMVAE_CHECK_ARG(B >= 0 && OH > 0 && OW > 0 && C > 0 && C % 8 == 0, "zero_insert2x: bad shape (C must be a multiple of 8)");
+    DMVAE_CHECK_ARG(((uintptr_t)dy & 15) == 0 && ((uintptr_t)dyz & 15) == 0, "zero_insert2x: buffers must be 16-byte aligned");
+    const int64_t n = B * 4 * OH * OW * (C / 8);
+    if (n == 0) return DMVAE_OK;
+    zero_insert2x_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (uint4*)dyz, B, OH, OW, C / 8);
+    DMVAE_CHECK_LAUNCH("zero_insert2x_kernel");
+    return DMVAE_OK;
+}

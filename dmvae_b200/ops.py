@@ -88,6 +88,9 @@ def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[tor
         call("dmvae_conv_tc_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), ptr(stats), B, H, W, cin, cout, kh, kw)
         if stats is not None:
             y._dmvae_gnstats = (stats, y.data_ptr(), tuple(y.shape), _ver(y))       # consumed by the next GroupNorm
+    elif (stride == 2 and residual is None and not force_direct
+          and query("dmvae_conv_tc_strided_supported", B, H, W, cin, OH, OW, cout, kh, kw, stride)):
+        call("dmvae_conv_tc_fwd_strided", ptr(x), ptr(w_packed), ptr(bias), ptr(y), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
     else:
         call("dmvae_conv_direct_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, OH, OW, cout,
              kh, kw, stride, pt, pl)
@@ -107,6 +110,12 @@ def conv_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, stride: 
         dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
         call("dmvae_wgrad_unpack", ptr(scratch), ptr(dw), cout, cin, kh * kw, 0)
         return dw
+    if stride == 2 and not force_direct and query("dmvae_conv_tc_strided_supported", B, H, W, cin, OH, OW, cout, kh, kw, stride):
+        scratch = torch.zeros((kh * kw, cout, cin), dtype=torch.float32, device=x.device)
+        call("dmvae_conv_tc_wgrad_strided", ptr(x), ptr(dy), ptr(scratch), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
+        dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
+        call("dmvae_wgrad_unpack", ptr(scratch), ptr(dw), cout, cin, kh * kw, 0)
+        return dw
     dw = torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
     call("dmvae_conv_direct_wgrad", ptr(x), ptr(dy), ptr(dw), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
     return dw
@@ -121,6 +130,12 @@ def conv_dgrad_raw(dy: torch.Tensor, w_fwd: torch.Tensor, w_dgrad: torch.Tensor,
     if stride == 1 and OH == H and OW == W:
         # "same" conv: dX = conv(dY, flipped/transposed weights) with the mirrored padding
         return conv_forward_raw(dy, w_dgrad, None, None, kh, kw, 1, (kh - 1 - pt, kw - 1 - pl), (H, W), force_direct)
+    if (stride == 2 and kh == 3 and kw == 3 and pt == 0 and pl == 0 and H == 2 * OH and W == 2 * OW and cout % 8 == 0
+            and not force_direct and query("dmvae_conv_tc_supported", B, H, W, cout, cin, 3, 3)):
+        # Downsample (pad (0,1,0,1)): dx = conv3x3_same(zero-inserted dy, flipped weights) on the tensor cores
+        dyz = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=dy.device)
+        call("dmvae_zero_insert2x", ptr(dy), ptr(dyz), B, OH, OW, cout)
+        return conv_forward_raw(dyz, w_dgrad, None, None, 3, 3, 1, (1, 1), (H, W))
     dx = torch.empty((B, H, W, cin), dtype=torch.bfloat16, device=dy.device)
     call("dmvae_conv_direct_dgrad_strided", ptr(dy), ptr(w_fwd), ptr(dx), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
     return dx

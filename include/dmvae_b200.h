@@ -120,6 +120,20 @@ int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int 
 int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
                       double* gn_stats, int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
 
+/* Stride-2 3x3 convolution (flux_ae.Downsample, :85-95: pad (0,1,0,1) => pad_top = pad_left = 0) on the tcgen05 tile:
+ * the A operand is sampled with TMA element strides, the right/bottom padding is the TMA out-of-bounds fill.
+ * Forward, weight gradient (tap-major scratch as dmvae_conv_tc_wgrad), and -- via dmvae_zero_insert2x + a stride-1
+ * dmvae_conv_tc_fwd with the dgrad weight pack -- the data gradient. */
+int dmvae_conv_tc_strided_supported(int B, int IH, int IW, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride);
+int dmvae_conv_tc_fwd_strided(const void* x, const void* w_packed, const float* bias, void* y, int B, int IH, int IW,
+                              int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad_top, int pad_left,
+                              void* stream);
+int dmvae_conv_tc_wgrad_strided(const void* x, const void* dy, float* dw_tap_major, int B, int IH, int IW, int Cin,
+                                int OH, int OW, int Cout, int KH, int KW, int stride, int pad_top, int pad_left,
+                                void* stream);
+/* dyz[b][2oh+1][2ow+1][c] = dy[b][oh][ow][c], zero elsewhere (bf16, C % 8 == 0). */
+int dmvae_zero_insert2x(const void* dy, void* dyz, int64_t B, int OH, int OW, int C, void* stream);
+
 /* Tuning / test hook (host only): 0 = heuristic, 1 = 128-pixel tiles per CTA, 2 = 256-pixel tiles where possible. */
 int dmvae_conv_tc_set_tile_mode(int mode);
 

@@ -351,6 +351,17 @@ def test_thin_head_gradients_as_gemms():
     assert rel_err(nchw(dx), xr.grad) < 4e-3 and rel_err(dw, wr.grad) < 1e-3
 
 
+@pytest.mark.parametrize("case", [
+    (2, 64, 64, 32, 32, 3, 2, (0, 0), False),       # Downsample at small width
+    (1, 128, 128, 64, 64, 3, 2, (0, 0), False),     # encoder level 0 -> 1
+    (2, 256, 256, 32, 64, 3, 2, (0, 0), False),     # pair kernel (Cout = 256), rectangular
+    (1, 512, 512, 32, 32, 3, 2, (0, 0), False),
+])
+def test_conv_tcgen05_stride2(case):
+    """flux_ae.Downsample on the tensor cores: TMA element strides (fwd, wgrad) and zero insertion (dgrad)."""
+    _conv_case(*case, force_direct=False)
+
+
 def test_conv_tc_many_tiles_matches_direct():
     """Full-size layer (512->512 @64x64, B=2: 128 pixel tiles x 2 N tiles): tensor-core path vs CUDA-core path on device."""
     ops, _ = _ops()
