@@ -142,6 +142,38 @@ def build_trainer(device, model_size="large", z_channels=32):
     return TokenizerTrainer(vae, VAELossFunction(cfg, lpips_loss=lp), lr=1e-4)
 
 
+class Stress512Trainer:
+    """BASELINE configs[4]: flux_ae Encoder -> reparameterize + KL -> Decoder at 512x512 (a synthetic stress harness,
+    the reference VAE hard-codes 256).  L1 + 1e-6*KL, fused clip/AdamW/EMA, gradient arena all-reduce."""
+
+    def __init__(self, dev, res=512):
+        from dmvae_b200 import losses
+        from dmvae_b200.autoencoder import Decoder, Encoder
+        from dmvae_b200.optim import FlatAdamWEMA
+        from dmvae_b200.train_arena import GradArena
+        from dmvae_b200.vae import init_weights
+        torch.manual_seed(42)
+        self.losses = losses
+        self.enc = Encoder(resolution=res, in_channels=3, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=16).to(dev)
+        self.dec = Decoder(ch=128, out_ch=3, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, resolution=res, z_channels=16).to(dev)
+        init_weights(self.enc, 0.02); init_weights(self.dec, 0.02)
+        self.arena = GradArena(list(self.enc.parameters()) + list(self.dec.parameters()))
+        self.opt = FlatAdamWEMA(self.arena.params, lr=1e-4, arena=self.arena)
+
+    def step(self, images):
+        self.arena.zero()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            h = self.enc(images)
+            eps = torch.randn(h.shape[0], h.shape[1] // 2, h.shape[2], h.shape[3], device=h.device, dtype=h.dtype)
+            z, kl = self.losses.reparam_kl(h, eps, channel_dim=1)
+            rec = self.dec(z).float()
+            l1, _ = self.losses.l1_l2_loss(rec, images)
+            loss = l1 + 1e-6 * kl
+        loss.backward()
+        self.arena.allreduce()
+        return {"loss": loss.detach(), "vae_norm": self.opt.step()}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from dmvae_b200 import _lib
@@ -154,10 +186,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.benchmark = True
     B = args.batch
-    tr = build_trainer(dev)
+    res = 256
+    if args.workload == "stress512":
+        res = 512
+        B = args.batch if args.batch != 16 else 4
+        tr = Stress512Trainer(dev, res)
+    else:
+        tr = build_trainer(dev)
     g = torch.Generator().manual_seed(42 * world + rank)
     n_pool = 4
-    host = [(torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).pin_memory() for _ in range(n_pool)]
+    host = [(torch.rand(B, 3, res, res, generator=g) * 2 - 1).pin_memory() for _ in range(n_pool)]
     resident = [h.to(dev) for h in host]
 
     def barrier():
@@ -236,11 +274,14 @@ def run_ours(args):
         "metric": METRIC, "value": round(imgs / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "train_tokenizer.py VAE pretrain step (BASELINE configs[1]): frozen ViT-L/16 encoder, flux Decoder "
-                               "fwd+bwd, L1+LPIPS(VGG16), allreduce, clip, AdamW, EMA", "per_gpu_batch": B, "global_batch": B * world,
-                   "image": "3x256x256", "z_channels": 32, "parallelism": f"dp{world}", "weights": "random init (seed 42)",
+        "config": {"workload": ("train_tokenizer.py VAE pretrain step (BASELINE configs[1]): frozen ViT-L/16 encoder, flux Decoder "
+                                "fwd+bwd, L1+LPIPS(VGG16), allreduce, clip, AdamW, EMA") if args.workload == "tokenizer" else
+                               ("BASELINE configs[4] stress: flux_ae Encoder -> reparam+KL -> Decoder fwd+bwd at 512x512, L1 + KL, "
+                                "allreduce, clip, AdamW, EMA"), "per_gpu_batch": B, "global_batch": B * world,
+                   "image": f"3x{res}x{res}", "z_channels": 32 if args.workload == "tokenizer" else 16, "parallelism": f"dp{world}",
+                   "weights": "random init (seed 42)",
                    "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; 4 rotating input batches"},
-        "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": B * 3 * 256 * 256 * 4,
+        "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": B * 3 * res * res * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last.get("loss")},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         "wgrad": {"achieved_tflops": round(wg[2] / (wg[1] * 1e-3) / 1e12, 1) if wg[1] else None, "launches_per_step": wg[0],
@@ -248,7 +289,7 @@ def run_ours(args):
         "profiled_step_ms": {"total": round(prof_total_ms, 3), "library_kernels": round(lib_ms, 3)},
         "kernels_ms_per_step": kernels,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "tokenizer":
         out["cpu_baseline"] = cpu_step_baseline(sample_images=1, reps=1)
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -339,6 +380,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tokenizer", choices=["tokenizer", "stress512"],
+                    help="tokenizer = BASELINE configs[1] (the headline workload); stress512 = configs[4] (no CPU baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
