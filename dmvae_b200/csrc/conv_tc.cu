@@ -428,7 +428,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     if (warp == 1) tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
-    cluster_sync_all();
+    __syncthreads();             // CTA-level ordering of the barrier inits / TMEM slot (the cluster barrier below subsumes it;
+    cluster_sync_all();          // kept explicit so compute-sanitizer racecheck sees the dependency)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
