@@ -67,13 +67,20 @@ class VAELossFunction:
         t = t * (a.t1 - a.t0) + a.t0
         xt = losses.dmd_mix_xt(latents_norm, x0, t)
         with torch.no_grad():
-            v_teacher = self.base_model(xt, t, labels)
-            v_student = self.sit_wo_ddp(xt, t, labels)
             vT_u = vS_u = None
-            if a.dmd_cfg_scale > 1:
-                uncond = torch.ones_like(labels) * a.num_classes
-                vT_u = self.base_model(xt, t, uncond)
-                vS_u = self.sit_wo_ddp(xt, t, uncond)
+            pair_T = getattr(self.base_model, "forward_cond_uncond", None)
+            pair_S = getattr(self.sit_wo_ddp, "forward_cond_uncond", None)
+            if a.dmd_cfg_scale > 1 and pair_T is not None and pair_S is not None:
+                # conditional + unconditional rows in one batched pass per network (2 forwards instead of 4)
+                v_teacher, vT_u = pair_T(xt, t, labels)
+                v_student, vS_u = pair_S(xt, t, labels)
+            else:
+                v_teacher = self.base_model(xt, t, labels)
+                v_student = self.sit_wo_ddp(xt, t, labels)
+                if a.dmd_cfg_scale > 1:
+                    uncond = torch.ones_like(labels) * a.num_classes
+                    vT_u = self.base_model(xt, t, uncond)
+                    vS_u = self.sit_wo_ddp(xt, t, uncond)
         loss, gnorm = losses.dmd_loss(latents_norm, xt, t, v_teacher, v_student, vT_u, vS_u, a.dmd_cfg_scale, True)
         return loss, {"dmd_loss": loss.detach(), "dmd_gradient_norm": gnorm}
 
@@ -95,6 +102,17 @@ class VAELossFunction:
 
 
 from .train_arena import GradArena  # noqa: E402,F401  (re-exported)
+
+
+def dit_training_loss(model: Callable, latents: torch.Tensor, labels: torch.Tensor, time_dist_shift: float = 1.0,
+                      cpu_generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Transport.training_losses for the linear path / velocity prediction (diffusion/transport/transport.py:119-142):
+    xt = t*x1 + (1-t)*x0, target ut = x1 - x0, loss = mean over batch of the per-sample mean squared error."""
+    t, x0 = sample_t_x0(latents, time_dist_shift, cpu_generator=cpu_generator)
+    xt = losses.dmd_mix_xt(latents, x0, t)
+    ut = latents - x0
+    out = model(xt, t, labels)
+    return ((out - ut) ** 2).flatten(1).mean(1).mean()
 
 
 @torch.no_grad()
@@ -143,4 +161,64 @@ class TokenizerTrainer:
         if self.ema is not None:
             update_ema(self.ema, [p.data for p in self.params])
         log["loss"] = loss.detach()
+        return log
+
+
+class DmdTrainer:
+    """One train_dmd.py iteration (:506-575) without the discriminator: the VAE turn (whole VAE trainable incl. the encoder,
+    :519; recon + LPIPS + dmd_weight * DMD; clip; AdamW) followed by the student-DiT flow-matching step (:563-575)."""
+
+    def __init__(self, vae: nn.Module, sit: nn.Module, base_model: nn.Module, lpips_loss: Optional[nn.Module], cfg: LossConfig,
+                 lr_vae: float = 2e-5, lr_sit: float = 1e-4, latent_mean: float = 0.0, latent_scale: float = 1.0):
+        self.vae, self.sit, self.base = vae, sit, base_model
+        self.cfg, self.latent_mean, self.latent_scale = cfg, latent_mean, latent_scale
+        self.loss_fn = VAELossFunction(cfg, lpips_loss=lpips_loss, sit=sit, base_model=base_model)
+        for p in base_model.parameters():
+            p.requires_grad = False
+        self.arena_vae = GradArena(vae.parameters())
+        self.arena_sit = GradArena(sit.parameters())
+        fused = self.arena_vae.params[0].is_cuda
+        self.opt_vae = torch.optim.AdamW(self.arena_vae.params, lr=lr_vae, betas=(0.9, 0.95), eps=1e-8, fused=fused)
+        self.opt_sit = torch.optim.AdamW(self.arena_sit.params, lr=lr_sit, betas=(0.9, 0.95), eps=1e-8, fused=fused)
+
+    @staticmethod
+    def _clip(arena: GradArena, max_norm: float = 1.0) -> torch.Tensor:
+        total = torch.linalg.vector_norm(arena.flat, 2)
+        arena.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        return total
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor, vae_turn: bool = True) -> Dict[str, torch.Tensor]:
+        dev = images.device.type
+        log: Dict[str, torch.Tensor] = {}
+        self.arena_vae.zero()
+        with torch.autocast(device_type=dev, dtype=torch.bfloat16):
+            if vae_turn:
+                recon, z = self.vae(images, return_latent=True)
+            else:
+                with torch.no_grad():
+                    z = self.vae.encode(images)
+            latents = latents_to_spatial((z - self.latent_mean) * self.latent_scale)
+            if vae_turn:
+                self.sit.eval()
+                for p in self.sit.parameters():
+                    p.requires_grad = False
+                loss, log = self.loss_fn.forward_generator(images, recon, latents, labels, compute_dmd=self.cfg.dmd_weight > 0)
+        if vae_turn:
+            loss.backward()
+            self.arena_vae.allreduce()
+            log["vae_norm"] = self._clip(self.arena_vae)
+            self.opt_vae.step()
+            log["loss"] = loss.detach()
+        # 2. train the student DiT on the (detached) latents
+        for p in self.sit.parameters():
+            p.requires_grad = True
+        self.sit.train()
+        self.arena_sit.zero()
+        with torch.autocast(device_type=dev, dtype=torch.bfloat16):
+            dloss = dit_training_loss(self.sit, latents.detach(), labels, self.cfg.time_dist_shift)
+        dloss.backward()
+        self.arena_sit.allreduce()
+        log["sit_norm"] = self._clip(self.arena_sit)
+        self.opt_sit.step()
+        log["diffusion_loss"] = dloss.detach()
         return log

@@ -202,7 +202,54 @@ def main():
     (dpts,) = torch.autograd.grad(loss, pts)
     cases["toy_fp32"] = dict(points=points, x0=x0, t=t, vT=vT, vS=vS, loss=loss.detach(), dpoints=dpts, grad=grad.detach())
     torch.save(cases, os.path.join(OUT, "dmd.pt"))
-    for f in ("flux_ae.pt", "lpips.pt", "dmd.pt"):
+    # --- N1: LightningDiT (tiny config + manifest of Mini/1) from the reference, timm / fairscale replaced by import shims
+    class _PE(torch.nn.Module):          # timm.models.vision_transformer.PatchEmbed as the reference uses it
+        def __init__(self, img_size, patch_size, in_chans, embed_dim, bias=True):
+            super().__init__()
+            self.patch_size = (patch_size, patch_size)
+            self.num_patches = (img_size // patch_size) ** 2
+            self.proj = torch.nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias)
+
+        def forward(self, x):
+            return self.proj(x).flatten(2).transpose(1, 2)
+
+    class _Mlp(torch.nn.Module):
+        def __init__(self, in_features, hidden_features, act_layer, drop=0):
+            super().__init__()
+            self.fc1, self.act, self.fc2 = torch.nn.Linear(in_features, hidden_features), act_layer(), torch.nn.Linear(hidden_features, in_features)
+
+        def forward(self, x):
+            return self.fc2(self.act(self.fc1(x)))
+    for name, attrs in {"timm": {}, "timm.models": {}, "timm.models.vision_transformer": {"PatchEmbed": _PE, "Mlp": _Mlp},
+                        "fairscale": {}, "fairscale.nn": {}, "fairscale.nn.model_parallel": {},
+                        "fairscale.nn.model_parallel.initialize": {"get_model_parallel_world_size": lambda: 1},
+                        "fairscale.nn.model_parallel.layers": {"ColumnParallelLinear": object, "ParallelEmbedding": object,
+                                                               "RowParallelLinear": object}}.items():
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(mod, k, v)
+            sys.modules[name] = mod
+    os.environ["TORCHDYNAMO_DISABLE"] = "1"
+    from diffusion.lightningdit import lightningdit as RD
+    torch.manual_seed(3)
+    dit = RD.LightningDiT(input_size=4, patch_size=1, in_channels=8, hidden_size=64, depth=2, num_heads=2, num_classes=10).eval()
+    gg = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for n, p_ in dit.named_parameters():          # the zero-initialised layers would make v == 0
+            if "adaLN_modulation" in n or "final_layer" in n or "norm" in n:
+                p_.copy_((1.0 if n.endswith("norm1.weight") or n.endswith("norm2.weight") or "norm_final" in n or "q_norm" in n or "k_norm" in n else 0.0)
+                         + 0.05 * torch.randn(p_.shape, generator=gg))
+    x = torch.randn(3, 8, 4, 4, generator=gg)
+    t = torch.rand(3, generator=gg)
+    y = torch.tensor([1, 7, 10])
+    with torch.no_grad():
+        v = dit(x, t, y)
+        v_unc = dit(x, t, torch.full_like(y, 10))
+    mini = RD.LightningDiT_Mini_1(input_size=16, in_channels=32, num_classes=1000)
+    torch.save(dict(sd={k: v_.clone() for k, v_ in dit.state_dict().items()}, x=x, t=t, y=y, v=v, v_unc=v_unc,
+                    manifest_mini={k: tuple(v_.shape) for k, v_ in mini.state_dict().items()}), os.path.join(OUT, "dit.pt"))
+    for f in ("flux_ae.pt", "lpips.pt", "dmd.pt", "dit.pt"):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 
 

@@ -357,3 +357,39 @@ def test_fused_clip_adamw_ema_matches_torch():
     for (k, ea), eb in zip(ema_a.items(), ema_b):
         assert rel(ea, eb) < 2e-6, k
     assert set(net_a.state_dict().keys()) == set(net_b.state_dict().keys())
+
+
+def test_dmd_stage_iteration_with_lightningdit():
+    """BASELINE configs[2]: a train_dmd.py iteration with LightningDiT-Mini/1 teacher and student (restated in dmvae_b200.dit,
+    pinned to the reference by tests/test_dit_cpu.py): VAE turn with the fused DMD loss, then the student flow-matching step."""
+    from dmvae_b200.dit import LightningDiT_Mini_1
+    from dmvae_b200.train import DmdTrainer, LossConfig
+    from dmvae_b200.vae import VAE
+    torch.manual_seed(0)
+    vae = VAE(z_channels=32, model_size="base").to(DEV)
+
+    def mk():
+        m = LightningDiT_Mini_1(input_size=16, in_channels=32, num_classes=1000)
+        for lin in (m.final_layer.linear, m.final_layer.adaLN_modulation[-1]):      # a fresh head outputs v = 0 (SURVEY D6)
+            torch.nn.init.normal_(lin.weight, std=0.02)
+        return m.to(DEV)
+    teacher, student = mk(), mk()
+    tr = DmdTrainer(vae, student, teacher, None, LossConfig(lpips=0.0, dmd_weight=10.0, dmd_cfg_scale=5.0))
+    x = torch.rand(2, 3, 256, 256, device=DEV) * 2 - 1
+    y = torch.randint(0, 1000, (2,), device=DEV)
+    # batched cond+uncond pass == two separate passes
+    xt = torch.randn(2, 32, 16, 16, device=DEV)
+    t = torch.rand(2, device=DEV)
+    with torch.no_grad():
+        vc, vu = teacher.eval().forward_cond_uncond(xt, t, y)
+        assert rel(vc, teacher(xt, t, y)) < 1e-4 and rel(vu, teacher(xt, t, torch.full_like(y, 1000))) < 1e-4
+    w0 = student.blocks[0].attn.qkv.weight.detach().clone()
+    e0 = vae.encoder.model.blocks[0].attn.qkv.weight.detach().clone()
+    log = tr.step(x, y, vae_turn=True)
+    for k in ("L1", "dmd_loss", "dmd_gradient_norm", "vae_norm", "diffusion_loss", "sit_norm"):
+        assert k in log and torch.isfinite(log[k]).all(), k
+    assert log["dmd_loss"].item() > 0
+    assert not torch.equal(student.blocks[0].attn.qkv.weight, w0)          # student stepped
+    assert not torch.equal(vae.encoder.model.blocks[0].attn.qkv.weight, e0)    # encoder is trainable in the DMD stage (:519)
+    log2 = tr.step(x, y, vae_turn=False)
+    assert "diffusion_loss" in log2 and "dmd_loss" not in log2
