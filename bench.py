@@ -174,6 +174,42 @@ class Stress512Trainer:
         return {"loss": loss.detach(), "vae_norm": self.opt.step()}
 
 
+class DmdStageTrainer:
+    """BASELINE configs[2]: a train_dmd.py iteration with LightningDiT-Mini/1 teacher (frozen) and student -- VAE turn every
+    ``vae_train_every`` = 5 iterations (scripts/train_dmd.sh), the student flow-matching step every iteration.  ViT-B encoder
+    trainable (train_dmd.py:519), recon L1 + LPIPS + 10 * DMD(cfg 5)."""
+
+    def __init__(self, dev, vae_train_every=5):
+        import warnings
+        from dmvae_b200.dit import LightningDiT_Mini_1
+        from dmvae_b200.lpips import LPIPS
+        from dmvae_b200.train import DmdTrainer, LossConfig
+        from dmvae_b200.vae import VAE
+        torch.manual_seed(42)
+        vae = VAE(z_channels=32, model_size="large").to(dev)
+
+        def mk():
+            m = LightningDiT_Mini_1(input_size=16, in_channels=32, num_classes=1000)
+            for lin in (m.final_layer.linear, m.final_layer.adaLN_modulation[-1]):   # zero-init head would give v = 0 everywhere
+                torch.nn.init.normal_(lin.weight, std=0.02)
+            return m.to(dev)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            lp = LPIPS(pretrained_vgg=False).eval().to(dev)
+        self.tr = DmdTrainer(vae, mk(), mk(), lp, LossConfig(l1=1.0, lpips=1.0, dmd_weight=10.0, dmd_cfg_scale=5.0))
+        self.every, self.it = vae_train_every, 0
+        self.labels = None
+
+    def step(self, images):
+        if self.labels is None or self.labels.shape[0] != images.shape[0]:
+            self.labels = torch.randint(0, 1000, (images.shape[0],), device=images.device)
+        turn = self.it % self.every == 0
+        self.it += 1
+        log = self.tr.step(images, self.labels, vae_turn=turn)
+        log.setdefault("loss", log["diffusion_loss"])
+        return log
+
+
 def run_ours(args):
     import torch.distributed as dist
     from dmvae_b200 import _lib
@@ -191,6 +227,10 @@ def run_ours(args):
         res = 512
         B = args.batch if args.batch != 16 else 4
         tr = Stress512Trainer(dev, res)
+    elif args.workload == "dmd":
+        tr = DmdStageTrainer(dev)
+        if args.steps % tr.every:
+            args.steps += tr.every - args.steps % tr.every        # whole vae_train_every cycles inside the timed region
     else:
         tr = build_trainer(dev)
     g = torch.Generator().manual_seed(42 * world + rank)
@@ -216,7 +256,7 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for i in range(args.warmup):
+    for i in range(args.warmup if args.workload != "dmd" else 2 * tr.every):
         tr.step(resident[i % n_pool])
     sampler = ClockSampler(local)
     if rank == 0:
@@ -232,7 +272,8 @@ def run_ours(args):
     def e2e_step(i):
         x = host[i % n_pool].to(dev, non_blocking=True)
         last["loss"] = tr.step(x)["loss"].item()
-    e2e_step(0)
+    for i in range(1 if args.workload != "dmd" else tr.every):
+        e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
 
     # one profiled step: CUDA events around every library launch
@@ -241,7 +282,7 @@ def run_ours(args):
     _lib.Stats.timing = True
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
-    tr.step(resident[0])
+    tr.step(resident[0])                         # (dmd workload: the iteration counter is back at a VAE turn here)
     pe1.record()
     torch.cuda.synchronize()
     _lib.Stats.timing = False
@@ -274,11 +315,16 @@ def run_ours(args):
         "metric": METRIC, "value": round(imgs / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": ("train_tokenizer.py VAE pretrain step (BASELINE configs[1]): frozen ViT-L/16 encoder, flux Decoder "
-                                "fwd+bwd, L1+LPIPS(VGG16), allreduce, clip, AdamW, EMA") if args.workload == "tokenizer" else
-                               ("BASELINE configs[4] stress: flux_ae Encoder -> reparam+KL -> Decoder fwd+bwd at 512x512, L1 + KL, "
-                                "allreduce, clip, AdamW, EMA"), "per_gpu_batch": B, "global_batch": B * world,
-                   "image": f"3x{res}x{res}", "z_channels": 32 if args.workload == "tokenizer" else 16, "parallelism": f"dp{world}",
+        "config": {"workload": {
+            "tokenizer": "train_tokenizer.py VAE pretrain step (BASELINE configs[1]): frozen ViT-L/16 encoder, flux Decoder "
+                         "fwd+bwd, L1+LPIPS(VGG16), allreduce, clip, AdamW, EMA",
+            "stress512": "BASELINE configs[4] stress: flux_ae Encoder -> reparam+KL -> Decoder fwd+bwd at 512x512, L1 + KL, "
+                         "allreduce, clip, AdamW, EMA",
+            "dmd": "train_dmd.py iteration (BASELINE configs[2]): LightningDiT-Mini/1 teacher+student; every 5th iteration is a VAE "
+                   "turn (trainable ViT-L/16 encoder + flux Decoder fwd+bwd, L1+LPIPS+10*DMD cfg 5), every iteration a student "
+                   "flow-matching step; allreduce, clip, AdamW per network; steps rounded up to whole 5-iteration cycles"}[args.workload],
+                   "per_gpu_batch": B, "global_batch": B * world,
+                   "image": f"3x{res}x{res}", "z_channels": 16 if args.workload == "stress512" else 32, "parallelism": f"dp{world}",
                    "weights": "random init (seed 42)",
                    "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; 4 rotating input batches"},
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": B * 3 * res * res * 4,
@@ -380,8 +426,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="tokenizer", choices=["tokenizer", "stress512"],
-                    help="tokenizer = BASELINE configs[1] (the headline workload); stress512 = configs[4] (no CPU baseline)")
+    ap.add_argument("--workload", default="tokenizer", choices=["tokenizer", "stress512", "dmd"],
+                    help="tokenizer = BASELINE configs[1] (the headline workload); dmd = configs[2]; stress512 = configs[4] "
+                         "(no CPU baseline for the last two)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -169,7 +169,8 @@ class DmdTrainer:
     :519; recon + LPIPS + dmd_weight * DMD; clip; AdamW) followed by the student-DiT flow-matching step (:563-575)."""
 
     def __init__(self, vae: nn.Module, sit: nn.Module, base_model: nn.Module, lpips_loss: Optional[nn.Module], cfg: LossConfig,
-                 lr_vae: float = 2e-5, lr_sit: float = 1e-4, latent_mean: float = 0.0, latent_scale: float = 1.0):
+                 lr_vae: float = 2e-5, lr_sit: float = 2e-5, latent_mean: float = 0.0, latent_scale: float = 1.0,
+                 wd: float = 0.005, fused_optimizer: bool = True):
         self.vae, self.sit, self.base = vae, sit, base_model
         self.cfg, self.latent_mean, self.latent_scale = cfg, latent_mean, latent_scale
         self.loss_fn = VAELossFunction(cfg, lpips_loss=lpips_loss, sit=sit, base_model=base_model)
@@ -177,14 +178,23 @@ class DmdTrainer:
             p.requires_grad = False
         self.arena_vae = GradArena(vae.parameters())
         self.arena_sit = GradArena(sit.parameters())
-        fused = self.arena_vae.params[0].is_cuda
-        self.opt_vae = torch.optim.AdamW(self.arena_vae.params, lr=lr_vae, betas=(0.9, 0.95), eps=1e-8, fused=fused)
-        self.opt_sit = torch.optim.AdamW(self.arena_sit.params, lr=lr_sit, betas=(0.9, 0.95), eps=1e-8, fused=fused)
+        self.fused = fused_optimizer and self.arena_vae.params[0].is_cuda
+        if self.fused:          # clip + AdamW in two kernels per network over the flat arenas (train_dmd.py has no EMA)
+            from .optim import FlatAdamWEMA
+            kw = dict(betas=(0.9, 0.95), eps=1e-8, weight_decay=wd, max_norm=1.0, ema_decay=None)
+            self.opt_vae = FlatAdamWEMA(self.arena_vae.params, lr=lr_vae, arena=self.arena_vae, **kw)
+            self.opt_sit = FlatAdamWEMA(self.arena_sit.params, lr=lr_sit, arena=self.arena_sit, **kw)
+        else:
+            self.opt_vae = torch.optim.AdamW(self.arena_vae.params, lr=lr_vae, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd)
+            self.opt_sit = torch.optim.AdamW(self.arena_sit.params, lr=lr_sit, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd)
 
-    @staticmethod
-    def _clip(arena: GradArena, max_norm: float = 1.0) -> torch.Tensor:
+    def _clip_step(self, arena: GradArena, opt, max_norm: float = 1.0) -> torch.Tensor:
+        """clip_grad_norm_(params, 1.0); optimizer.step() (train_dmd.py:540-542, :568-570)."""
+        if self.fused:
+            return opt.step()
         total = torch.linalg.vector_norm(arena.flat, 2)
         arena.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        opt.step()
         return total
 
     def step(self, images: torch.Tensor, labels: torch.Tensor, vae_turn: bool = True) -> Dict[str, torch.Tensor]:
@@ -206,8 +216,7 @@ class DmdTrainer:
         if vae_turn:
             loss.backward()
             self.arena_vae.allreduce()
-            log["vae_norm"] = self._clip(self.arena_vae)
-            self.opt_vae.step()
+            log["vae_norm"] = self._clip_step(self.arena_vae, self.opt_vae)
             log["loss"] = loss.detach()
         # 2. train the student DiT on the (detached) latents
         for p in self.sit.parameters():
@@ -218,7 +227,6 @@ class DmdTrainer:
             dloss = dit_training_loss(self.sit, latents.detach(), labels, self.cfg.time_dist_shift)
         dloss.backward()
         self.arena_sit.allreduce()
-        log["sit_norm"] = self._clip(self.arena_sit)
-        self.opt_sit.step()
+        log["sit_norm"] = self._clip_step(self.arena_sit, self.opt_sit)
         log["diffusion_loss"] = dloss.detach()
         return log
