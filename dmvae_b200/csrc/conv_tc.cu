@@ -519,6 +519,325 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------- halo-resident CTA-pair variant (3x3 and larger filters)
+// tcgen05 applies the 128-byte swizzle to ABSOLUTE shared-memory address bits (probed on B200: a K-major SW128 operand may
+// start at any 128-byte row of a TMA-written tile and use a stride-byte-offset that is not a multiple of 1024 B --
+// scripts/experiments/umma_rowshift_probe.cu).  So ONE (BH+KH-1) x (BW+KW-1) pixel halo of 64 channels, fetched once, serves
+// all KH*KW filter taps: tap (kh, kw) is the same tile read from row (kh*HP + kw) on, with the 8-pixel groups HP*128 B apart
+// (pixel tile = BH rows of exactly 8 pixels, HP = 8 + KW - 1).  Per 64-channel chunk of a 3x3 conv each CTA writes
+// 23 KB (halo) + 9 weight half-tiles into shared memory instead of 9 x (16 KB + weight half-tile): for N = 256 the operand
+// bytes pulled from L2 and written to shared memory drop by 42 %, for N = 128 by 57 %, which is what bounds these tiles.
+// Pipeline: a ring of halo slots (one per tile x channel chunk) and a ring of weight slots (one per tap), each with its
+// own full/empty barriers; loop order is chunk-outer / tap-inner.  Otherwise identical to conv_tc2_kernel.
+constexpr int HALO_W = 8;       // pixels per tile row = rows per swizzle group
+constexpr int HALO_H = 16;
+
+template <int BN> struct CfgH {
+    static constexpr int A_SLOT = 40 * 1024;                    // largest halo: 5x5 filter -> 20 x 12 px x 128 B = 30 KB (3x3: 22.5 KB)
+    static constexpr int A_SLOT3 = 23 * 1024;                   // 3x3: 18 x 10 px x 128 B = 23040 B, rounded to 1024
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;           // this CTA's half of one tap's weight tile
+    static constexpr int SA = BN == 256 ? 3 : 4;
+    static constexpr int SB = (200 * 1024 - SA * A_SLOT3) / B_BYTES > 12 ? 12 : (200 * 1024 - SA * A_SLOT3) / B_BYTES;
+    static constexpr int SMEM_BYTES = SA * A_SLOT3 + SB * B_BYTES + 1024 + 512;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;
+    static constexpr int THREADS = 192;
+};
+
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out,
+                 double* __restrict__ stats, TcGeom g) {
+    using C = CfgH<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_b = smem + C::SA * C::A_SLOT3;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::SB * C::B_BYTES);
+    uint64_t* afull = bars;                            // [SA]   (leader's copies are the live ones for full / tempty)
+    uint64_t* aempty = afull + C::SA;                  // [SA]
+    uint64_t* bfull = aempty + C::SA;                  // [SB]
+    uint64_t* bempty = bfull + C::SB;                  // [SB]
+    uint64_t* tfull = bempty + C::SB;                  // [2]
+    uint64_t* tempty = tfull + 2;                      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int pair_tiles = (g.m_tiles >> 1) * g.n_tiles;
+    const int taps = g.KH * g.KW;
+    const int HP = HALO_W + g.KW - 1;                              // halo pitch in pixels
+    const uint32_t halo_bytes = (uint32_t)((HALO_H + g.KH - 1) * HP * 128);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int s = 0; s < C::SA; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < C::SB; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer (both CTAs) ==============================
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+                const int mt = 2 * (pt / g.n_tiles) + (int)rank, nt = pt % g.n_tiles;
+                const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
+                const int w0 = tw * HALO_W - g.pl, h0 = th * HALO_H - g.pt, n0 = nt * BN + (int)rank * (BN / 2);
+                for (int kc = 0; kc < g.k_chunks; ++kc) {
+                    mbar_wait(&aempty[sa], pa ^ 1);
+                    if (leader) mbar_expect_tx(&afull[sa], 2 * halo_bytes);
+                    tma_load_4d_2sm(smem + sa * C::A_SLOT3, &map_a, mapa_u32(smem_u32(&afull[sa]), 0), kc * BK, w0, h0, b);
+                    if (++sa == C::SA) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&bempty[sb], pb ^ 1);
+                        if (leader) mbar_expect_tx(&bfull[sb], 2 * C::B_BYTES);
+                        tma_load_3d_2sm(smem_b + sb * C::B_BYTES, &map_b, mapa_u32(smem_u32(&bfull[sb]), 0), kc * BK, n0, tap);
+                        if (++sb == C::SB) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer (leader only) ==============================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_m256(BN);
+            const uint32_t sbo = (uint32_t)HP * 128;
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int kc = 0; kc < g.k_chunks; ++kc) {
+                    mbar_wait(&afull[sa], pa);
+                    const uint32_t a_base = smem_u32(smem + sa * C::A_SLOT3);
+                    int kh = 0, kw = 0;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&bfull[sb], pb);
+                        tc_fence_after();
+                        const uint64_t adesc = make_kmajor_sw128_desc_sbo(a_base + (uint32_t)(kh * HP + kw) * 128, sbo);
+                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem_b + sb * C::B_BYTES));
+#pragma unroll
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                            umma_bf16_2sm(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kc | tap | kk) != 0);
+                        umma_commit_2sm(&bempty[sb]);
+                        if (++sb == C::SB) { sb = 0; pb ^= 1; }
+                        if (++kw == g.KW) { kw = 0; ++kh; }
+                    }
+                    umma_commit_2sm(&aempty[sa]);                   // halo slot free once the last tap's MMAs retire
+                    if (++sa == C::SA) { sa = 0; pa ^= 1; }
+                }
+                umma_commit_2sm(&tfull[buf]);
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5, both CTAs) ==============================
+        const int lg = warp & 3;
+        const int r = lg * 32 + lane;
+        const int dh = r / HALO_W, dw = r % HALO_W;
+        int it = 0;
+        for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++it) {
+            const int buf = it & 1;
+            const int mt = 2 * (pt / g.n_tiles) + (int)rank, nt = pt % g.n_tiles;
+            const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
+            const int64_t pix = ((int64_t)b * g.H + th * HALO_H + dh) * g.W + tw * HALO_W + dw;
+            const int n0 = nt * BN;
+            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                epilogue_chunk(v, n0 + c0, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0));
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------- transposed halo tile for 128-channel outputs
+// Measured on B200 (scripts/experiments/umma_pace_probe.cu): a shared-memory-operand tcgen05.mma with M = 128 rows per CTA
+// retires one instruction per ~140 cycles whatever N is (the 128 x 32 B A-operand read paces it), so an N = 128 instruction
+// runs the tensor pipe at half rate and only N = 256 reaches the peak.  For Cout = 128 layers the GEMM is therefore issued
+// transposed:   D^T[co, pixel] = sum_{tap, ci} Wp[tap][co][ci] * X[pixel (+) tap, ci]        M = 128 (Cout), N = 256 (pixels)
+// A = the weight tile of one tap (the same TMA box as before, now the A operand), B = 256 pixels = 32 image rows x 8 pixels
+// read straight out of one (32+2) x (8+2) pixel halo (see conv_tc2h_kernel) at the tap's row offset.  The accumulator holds
+// channels in TMEM lanes and pixels in columns; the epilogue writes it back to channels-last memory as 64-byte segments
+// (32 consecutive channels of one pixel per warp store).
+constexpr int THALO_H = 32;
+struct CfgT {
+    static constexpr int A_SLOT = 43 * 1024;                    // (32+2) x (8+2) px x 128 B = 43520 B
+    static constexpr int W_BYTES = BM * BK * 2;                 // one tap's weight tile: 128 co x 64 ci
+    static constexpr int SA = 2, SW = 7;
+    static constexpr int SMEM_BYTES = SA * A_SLOT + SW * W_BYTES + 1024 + 512;
+    static constexpr uint32_t TMEM_COLS = 512;                  // two accumulator buffers of 256 pixel columns
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+};
+
+__global__ void __launch_bounds__(CfgT::THREADS, 1)
+conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out, TcGeom g) {
+    using C = CfgT;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_w = smem + C::SA * C::A_SLOT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + C::SW * C::W_BYTES);
+    uint64_t* afull = bars;
+    uint64_t* aempty = afull + C::SA;
+    uint64_t* wfull = aempty + C::SA;
+    uint64_t* wempty = wfull + C::SW;
+    uint64_t* tfull = wempty + C::SW;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = g.m_tiles * g.n_tiles;              // m_tiles: 256-pixel tiles, n_tiles: 128-channel tiles
+    const int taps = g.KH * g.KW;
+    const int HP = HALO_W + g.KW - 1;
+    const uint32_t halo_bytes = (uint32_t)((THALO_H + g.KH - 1) * HP * 128);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_x);
+        prefetch_tmap(&map_w);
+        for (int s = 0; s < C::SA; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < C::SW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], C::EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sa = 0, sw = 0; uint32_t pa = 0, pw = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
+                const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
+                const int w0 = tw * HALO_W - g.pl, h0 = th * THALO_H - g.pt, co0 = nt * BM;
+                for (int kc = 0; kc < g.k_chunks; ++kc) {
+                    mbar_wait(&aempty[sa], pa ^ 1);
+                    mbar_expect_tx(&afull[sa], halo_bytes);
+                    tma_load_4d(smem + sa * C::A_SLOT, &map_x, &afull[sa], kc * BK, w0, h0, b);
+                    if (++sa == C::SA) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&wempty[sw], pw ^ 1);
+                        mbar_expect_tx(&wfull[sw], C::W_BYTES);
+                        tma_load_3d(smem_w + sw * C::W_BYTES, &map_w, &wfull[sw], kc * BK, co0, tap);
+                        if (++sw == C::SW) { sw = 0; pw ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(256);           // M = 128 channels, N = 256 pixels
+            const uint32_t sbo = (uint32_t)HP * 128;
+            int sa = 0, sw = 0; uint32_t pa = 0, pw = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kc = 0; kc < g.k_chunks; ++kc) {
+                    mbar_wait(&afull[sa], pa);
+                    const uint32_t x_base = smem_u32(smem + sa * C::A_SLOT);
+                    int kh = 0, kw = 0;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&wfull[sw], pw);
+                        tc_fence_after();
+                        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem_w + sw * C::W_BYTES));
+                        const uint64_t bdesc = make_kmajor_sw128_desc_sbo(x_base + (uint32_t)(kh * HP + kw) * 128, sbo);
+#pragma unroll
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                            umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kc | tap | kk) != 0);
+                        umma_commit(&wempty[sw]);
+                        if (++sw == C::SW) { sw = 0; pw ^= 1; }
+                        if (++kw == g.KW) { kw = 0; ++kh; }
+                    }
+                    umma_commit(&aempty[sa]);
+                    if (++sa == C::SA) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&tfull[buf]);
+            }
+        }
+    } else {
+        // ============================== epilogue: lane = channel, register = pixel ==============================
+        const int lg = warp & 3;                       // TMEM lanes [32*lg, 32*lg+32) = channels co0 + 32*lg + lane
+        const int half = (warp - 2) >> 2;              // pixel columns [128*half, 128*half+128)
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
+            const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
+            const int co = nt * BM + lg * 32 + lane;
+            const float bv = bias ? __ldg(bias + co) : 0.f;
+            const int64_t pix0 = ((int64_t)b * g.H + th * THALO_H) * g.W + tw * HALO_W;
+            mbar_wait(&tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * 256 + half * 128;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                const int n0 = half * 128 + c0;        // 32 pixel columns = 4 image rows of 8 pixels
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int64_t idx = (pix0 + (int64_t)((n0 + j) >> 3) * g.W + ((n0 + j) & 7)) * g.Cout + co;
+                    float f = __uint_as_float(v[j]) + bv;
+                    if (res) f = bf16_round(f) + __bfloat162float(res[idx]);
+                    out[idx] = __float2bfloat16_rn(f);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------- weight gradient
 // dWp[tap][co][ci] += sum_pixels dY[p][co] * X[p (+) tap][ci]          M = Cout, N = Cin, K = pixels (split)
 //
@@ -833,9 +1152,59 @@ int launch_conv_tc2(const void* x, const void* w, const float* bias, const void*
     return DMVAE_OK;
 }
 
+template <int BN>
+int launch_conv_tc2h(const void* x, const void* w, const float* bias, const void* res, void* y, double* stats, TcGeom g, cudaStream_t st) {
+    using C = CfgH<BN>;
+    CUtensorMap ma, mb;
+    const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
+    const uint32_t abox[4] = {BK, (uint32_t)(HALO_W + g.KW - 1), (uint32_t)(HALO_H + g.KH - 1), 1};
+    int rc = get_tensor_map(x, 4, adims, abox, &ma);
+    if (rc) return rc;
+    const uint64_t bdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, (uint64_t)(g.KH * g.KW)};
+    const uint32_t bbox[3] = {BK, BN / 2, 1};
+    rc = get_tensor_map(w, 3, bdims, bbox, &mb);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2h_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return dmvae_set_error(DMVAE_ECUDA, "conv_tc2h: smem attribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int pair_tiles = (g.m_tiles / 2) * g.n_tiles;
+    const int clusters = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
+    conv_tc2h_kernel<BN><<<2 * clusters, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, stats, g);
+    DMVAE_CHECK_LAUNCH("conv_tc2h_kernel");
+    return DMVAE_OK;
+}
+
+int launch_conv_tcT(const void* x, const void* w, const float* bias, const void* res, void* y, TcGeom g, cudaStream_t st) {
+    using C = CfgT;
+    CUtensorMap mx, mw;
+    const uint64_t xdims[4] = {(uint64_t)g.Cin, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
+    const uint32_t xbox[4] = {BK, (uint32_t)(HALO_W + g.KW - 1), (uint32_t)(THALO_H + g.KH - 1), 1};
+    int rc = get_tensor_map(x, 4, xdims, xbox, &mx);
+    if (rc) return rc;
+    const uint64_t wdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, (uint64_t)(g.KH * g.KW)};
+    const uint32_t wbox[3] = {BK, BM, 1};
+    rc = get_tensor_map(w, 3, wdims, wbox, &mw);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tcT_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return dmvae_set_error(DMVAE_ECUDA, "conv_tcT: smem attribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int tiles = g.m_tiles * g.n_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    conv_tcT_kernel<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mx, mw, bias, (const bf16*)res, (bf16*)y, g);
+    DMVAE_CHECK_LAUNCH("conv_tcT_kernel");
+    return DMVAE_OK;
+}
+
 // 0 = let the heuristic decide, 1 / 2 = force the number of 128-pixel sub-tiles per CTA, 3 = force CTA pairs
 int g_force_mt = 0;
 int g_pair_default = 1;      // CTA pairs for the N = 256 tiles (measured +10..30 % over the single-CTA tiles); mode 5 turns it off
+int g_halo = 1;              // halo-resident pair tiles for 3x3 filters (modes 6 / 7 turn it off / on)
 
 }  // namespace
 
@@ -883,6 +1252,27 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     }
     if (g_force_mt == 1) mt = 1;
     if (g_force_mt == 2 && bn >= 128 && pick_pixel_tile_n(H, W, 2 * BM, &bw2, &bh2)) mt = 2;
+    // transposed halo tiles for 128-channel outputs (an N = 128 instruction only half-fills the tensor pipe)
+    if (g_halo && (g_force_mt == 0 || g_halo == 2) && KH == 3 && KW == 3 && bn == 128 && Cout % BM == 0 && Cin % BK == 0 && !stats &&
+        W % HALO_W == 0 && H % THALO_H == 0) {
+        TcGeom gt = g;
+        gt.BW = HALO_W; gt.BH = THALO_H;
+        gt.tiles_w = W / HALO_W; gt.tiles_h = H / THALO_H;
+        gt.m_tiles = B * gt.tiles_w * gt.tiles_h;
+        gt.n_tiles = Cout / BM;
+        if (g_halo == 2 || gt.m_tiles * gt.n_tiles >= (num_sms() * 3) / 4)
+            return launch_conv_tcT(x, w_packed, bias, residual, y, gt, st);
+    }
+    // halo-resident CTA pairs: 3x3 filters, 16 x 8 pixel tiles, full N tiles, at least ~3/8 of a wave of pair tiles
+    if (g_halo && (g_force_mt == 0 || g_halo == 2) && KH == 3 && KW == 3 && bn >= 128 && Cout % bn == 0 && Cin % BK == 0 && W % HALO_W == 0 && H % HALO_H == 0) {
+        TcGeom gh = g;
+        gh.BW = HALO_W; gh.BH = HALO_H;
+        gh.tiles_w = W / HALO_W; gh.tiles_h = H / HALO_H;
+        gh.m_tiles = B * gh.tiles_w * gh.tiles_h;
+        if (gh.m_tiles % 2 == 0 && (g_halo == 2 || (gh.m_tiles / 2) * gh.n_tiles >= (num_sms() * 3) / 8))
+            return bn == 256 ? launch_conv_tc2h<256>(x, w_packed, bias, residual, y, stats, gh, st)
+                             : launch_conv_tc2h<128>(x, w_packed, bias, residual, y, stats, gh, st);
+    }
     // CTA pairs: 128-pixel tiles per CTA, an even number of them, full N tiles
     if (bn >= 128 && Cout % bn == 0 && (g_force_mt == 3 || (g_force_mt == 0 && g_pair_default && bn == 256))) {
         TcGeom gp = g;
@@ -987,6 +1377,9 @@ DMVAE_API int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_m
 DMVAE_API int dmvae_conv_tc_set_tile_mode(int mode) {
     if (mode == 4) { g_pair_default = 1; g_force_mt = 0; return DMVAE_OK; }      // heuristic, CTA pairs preferred
     if (mode == 5) { g_pair_default = 0; g_force_mt = 0; return DMVAE_OK; }      // heuristic, single-CTA tiles only
+    if (mode == 6) { g_halo = 0; return DMVAE_OK; }                              // per-tap operand fetch (no halo reuse)
+    if (mode == 7) { g_halo = 1; return DMVAE_OK; }
+    if (mode == 8) { g_halo = 2; return DMVAE_OK; }                              // halo tiles wherever the shape allows (tests)
     g_force_mt = (mode >= 1 && mode <= 3) ? mode : 0;
     return DMVAE_OK;
 }
