@@ -959,7 +959,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-                for (int tp = 0; tp < ntap; ++tp) {
+                for (int tp = 0; tp < ntap;) {
+                    // An M = 128 instruction takes ~140 cycles whatever N is (umma_pace_probe.cu), so 128-channel taps are issued
+                    // two at a time: their boxes are consecutive 64-channel atoms LBO apart, i.e. one N = 256 operand, and
+                    // their accumulators are adjacent TMEM column ranges.
+                    const bool two = (BN == 128) && (tp + 1 < ntap);
+                    const uint32_t id = two ? make_idesc_mn(256) : idesc;
                     const uint64_t bdesc = make_mnmajor_sw128_desc(sa + C::A_BYTES + tp * C::B_BYTES_TAP);
 #pragma unroll
                     for (int sub = 0; sub < MT; ++sub) {
@@ -968,9 +973,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
 #pragma unroll
                         for (int kk = 0; kk < WG_PIX / UMMA_K; ++kk) {
                             // 16 pixels = 16 rows of 128 B = 2048 B along K: +128 in 16-byte units
-                            umma_bf16(d_tmem, adesc + 128 * kk, bdesc + 128 * kk, idesc, (k | kk) != 0);
+                            umma_bf16(d_tmem, adesc + 128 * kk, bdesc + 128 * kk, id, (k | kk) != 0);
                         }
                     }
+                    tp += two ? 2 : 1;
                 }
                 umma_commit(&empty[stage]);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -1204,6 +1210,7 @@ int launch_conv_tcT(const void* x, const void* w, const float* bias, const void*
 // 0 = let the heuristic decide, 1 / 2 = force the number of 128-pixel sub-tiles per CTA, 3 = force CTA pairs
 int g_force_mt = 0;
 int g_pair_default = 1;      // CTA pairs for the N = 256 tiles (measured +10..30 % over the single-CTA tiles); mode 5 turns it off
+int g_wgrad_tpc = 3;         // taps per CTA of the 128-channel weight-gradient tile (modes 12 / 13 / 14 select 2 / 3 / 4)
 int g_halo = 1;              // halo-resident pair tiles for 3x3 filters (modes 6 / 7 turn it off / on)
 
 }  // namespace
@@ -1370,6 +1377,8 @@ DMVAE_API int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_m
     }
     if (wide_m) return launch_wgrad_tc<128, 2, 2>(x, dy, dw_tap_major, g, st);
     if (g_force_mt == 1) return launch_wgrad_tc<128, 1, 1>(x, dy, dw_tap_major, g, st);
+    if (g_wgrad_tpc == 2) return launch_wgrad_tc<128, 1, 2>(x, dy, dw_tap_major, g, st);
+    if (g_wgrad_tpc == 4) return launch_wgrad_tc<128, 1, 4>(x, dy, dw_tap_major, g, st);
     return launch_wgrad_tc<128, 1, 3>(x, dy, dw_tap_major, g, st);
 }
 
@@ -1379,7 +1388,8 @@ DMVAE_API int dmvae_conv_tc_set_tile_mode(int mode) {
     if (mode == 5) { g_pair_default = 0; g_force_mt = 0; return DMVAE_OK; }      // heuristic, single-CTA tiles only
     if (mode == 6) { g_halo = 0; return DMVAE_OK; }                              // per-tap operand fetch (no halo reuse)
     if (mode == 7) { g_halo = 1; return DMVAE_OK; }
-    if (mode == 8) { g_halo = 2; return DMVAE_OK; }                              // halo tiles wherever the shape allows (tests)
+    if (mode == 8) { g_halo = 2; return DMVAE_OK; }
+    if (mode >= 12 && mode <= 14) { g_wgrad_tpc = mode - 10; return DMVAE_OK; }                              // halo tiles wherever the shape allows (tests)
     g_force_mt = (mode >= 1 && mode <= 3) ? mode : 0;
     return DMVAE_OK;
 }

@@ -79,7 +79,7 @@ def main():
 
     if want("convtc"):
         from dmvae_b200 import _lib
-        shapes = [(64, 128, 128, 3), (128, 128, 128, 3), (512, 512, 32, 3), (512, 512, 64, 3), (512, 512, 128, 3), (512, 256, 128, 3), (256, 256, 128, 3), (256, 256, 256, 3),
+        shapes = [(64, 64, 256, 3), (64, 128, 128, 3), (128, 128, 128, 3), (128, 256, 64, 3), (512, 512, 32, 3), (512, 512, 64, 3), (512, 512, 128, 3), (512, 256, 128, 3), (256, 256, 128, 3), (256, 256, 256, 3),
                   (256, 128, 256, 3), (128, 128, 256, 3), (512, 512, 32, 1), (512, 256, 128, 1), (256, 128, 256, 1), (32, 512, 32, 3)]
         for cin, cout, hw, k in shapes:
             B = 16
@@ -102,6 +102,12 @@ def main():
                 _lib.query("dmvae_conv_tc_set_tile_mode", 7)
             us = timeit(lambda i: ops.conv_wgrad_raw(x, dy, k, k, 1, ((k - 1) // 2, (k - 1) // 2)), a.iters, 1)
             res["wgrad_tflops"] = round(flops / us / 1e6, 1)
+            if cin <= 128 and cout < 256:
+                for m in (12, 14):
+                    _lib.query("dmvae_conv_tc_set_tile_mode", m)
+                    us = timeit(lambda i: ops.conv_wgrad_raw(x, dy, k, k, 1, ((k - 1) // 2, (k - 1) // 2)), a.iters, 1)
+                    res[f"wgrad_tpc{m - 10}_tflops"] = round(flops / us / 1e6, 1)
+                _lib.query("dmvae_conv_tc_set_tile_mode", 13)
             print(json.dumps({"kernel": "conv_tc", "cin": cin, "cout": cout, "hw": hw, "k": k, "gflop": round(flops / 1e9, 1), **res}), flush=True)
             del x, dy
             torch.cuda.empty_cache()
