@@ -1020,6 +1020,135 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
     }
 }
 
+// ---------------------------------------------------------------- weight gradient, CTA-pair variant (cta_group::2)
+// ncu on the single-CTA kernel: tensor pipe 76 % active with sm__memory_throughput at the same 76 % -- the shared-memory
+// pipe (TMA writes + operand reads, ~146 B/cycle demanded of 128) is what holds it.  A CTA pair shares the x tile: each CTA
+// loads half of its 256 input channels and MT x 128 rows of dy; tcgen05.mma.cta_group::2 (M = 256) reads the two x halves
+// from both CTAs, so per SM the x bytes written to and read from shared memory halve (~101 B/cycle for MT = 2).
+template <int MT> struct Wg2Cfg {
+    static constexpr int A_BYTES = MT * 2 * WG_BOX_BYTES;       // dy: MT x 128 output channels of this CTA
+    static constexpr int B_BYTES = 2 * WG_BOX_BYTES;            // x: this CTA's 128 of the 256 input channels
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr uint32_t TMEM_COLS = MT * 256;
+    static constexpr int EPI_WARPS = 4 * MT;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+};
+
+template <int MT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Wg2Cfg<MT>::THREADS, 1)
+conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                      float* __restrict__ dwp, WgGeom g) {
+    using C = Wg2Cfg<MT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                        // leader's copies are live
+    uint64_t* empty = bars + C::STAGES;
+    uint64_t* tfull = bars + 2 * C::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    int id = blockIdx.x >> 1;
+    const int co_t = id % g.co_tiles; id /= g.co_tiles;       // co tile of the PAIR: 2 * MT * 128 output channels
+    const int ci_t = id % g.ci_tiles; id /= g.ci_tiles;
+    const int tap = id;
+    const int kh = tap / g.KW, kw = tap % g.KW;
+    const int co0 = co_t * (2 * MT * BM) + (int)rank * (MT * BM);
+    const int ci0 = ci_t * 256;
+    const int t_begin = blockIdx.y * g.tiles_per_split;
+    const int t_end = (t_begin + g.tiles_per_split < g.pix_tiles) ? t_begin + g.tiles_per_split : g.pix_tiles;
+    const int k_iters = t_end - t_begin;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_dy);
+        prefetch_tmap(&map_x);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, b = t / (g.tiles_w * g.tiles_h);
+                const int w0 = tw * g.BW, h0 = th * g.BH;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                uint8_t* sb = sa + C::A_BYTES;
+                if (leader) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+                const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+#pragma unroll
+                for (int j = 0; j < 2 * MT; ++j) tma_load_4d_2sm(sa + j * WG_BOX_BYTES, &map_dy, lbar, co0 + j * 64, w0, h0, b);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    tma_load_4d_2sm(sb + j * WG_BOX_BYTES, &map_x, lbar, ci0 + (int)rank * 128 + j * 64,
+                                    w0 * g.stride + kw - g.pl, h0 * g.stride + kh - g.pt, b);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_m256(256) | (1u << 15) | (1u << 16);      // M = 256 (pair), N = 256, both MN-major
+            int stage = 0; uint32_t phase = 0;
+            for (int k = 0; k < k_iters; ++k) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                const uint64_t bdesc = make_mnmajor_sw128_desc(sa + C::A_BYTES);
+#pragma unroll
+                for (int sub = 0; sub < MT; ++sub) {
+                    const uint64_t adesc = make_mnmajor_sw128_desc(sa + sub * 2 * WG_BOX_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < WG_PIX / UMMA_K; ++kk)
+                        umma_bf16_2sm(tmem_base + sub * 256, adesc + 128 * kk, bdesc + 128 * kk, idesc, (k | kk) != 0);
+                }
+                umma_commit_2sm(&empty[stage]);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit_2sm(tfull);
+        }
+    } else {
+        const int lg = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const int co = co0 + sub * BM + lg * 32 + lane;
+        if (k_iters > 0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + sub * 256;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                const int ci = ci0 + c0;
+                if (co < g.Cout && ci + 32 <= g.Cin) {
+                    float* dst = dwp + ((int64_t)tap * g.Cout + co) * g.Cin + ci;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    }
+}
+
 // ---------------------------------------------------------------- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1345,6 +1474,45 @@ int launch_wgrad_tc(const void* x, const void* dy, float* dwp, WgGeom g, cudaStr
     DMVAE_CHECK_LAUNCH("conv_tc_wgrad_kernel");
     return DMVAE_OK;
 }
+template <int MT>
+int launch_wgrad_tc2(const void* x, const void* dy, float* dwp, WgGeom g, cudaStream_t st) {
+    using C = Wg2Cfg<MT>;
+    CUtensorMap mdy, mx;
+    const uint32_t box[4] = {64, (uint32_t)g.BW, (uint32_t)g.BH, 1};
+    const uint64_t ddims[4] = {(uint64_t)g.Cout, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    int rc = get_tensor_map(dy, 4, ddims, box, &mdy);
+    if (rc) return rc;
+    const uint64_t xdims[4] = {(uint64_t)g.Cin, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
+    const uint32_t xstr[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
+    rc = get_tensor_map(x, 4, xdims, box, &mx, xstr);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad2_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return dmvae_set_error(DMVAE_ECUDA, "conv_tc_wgrad2: smem attribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    g.co_tiles = g.Cout / (2 * MT * BM);
+    g.ci_tiles = g.Cin / 256;
+    g.tap_groups = g.KH * g.KW;
+    const int base = g.co_tiles * g.ci_tiles * g.tap_groups;           // clusters before the pixel split
+    int splits = (num_sms() / 2) / base;
+    if (splits > g.pix_tiles) splits = g.pix_tiles;
+    if (splits < 1) splits = 1;
+    g.tiles_per_split = (g.pix_tiles + splits - 1) / splits;
+    g.splits = (g.pix_tiles + g.tiles_per_split - 1) / g.tiles_per_split;
+    dim3 grid((unsigned)(2 * base), (unsigned)g.splits);
+    conv_tc_wgrad2_kernel<MT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mdy, mx, dwp, g);
+    DMVAE_CHECK_LAUNCH("conv_tc_wgrad2_kernel");
+    return DMVAE_OK;
+}
+// CTA pairs for the weight gradient: 256-channel input tiles, whole 256- or 512-row output-channel blocks
+int wgrad_pair_mt(int Cin, int Cout) {
+    if (!g_pair_default || g_force_mt == 1 || g_force_mt == 2 || Cin % 256 != 0) return 0;
+    if (Cout % 512 == 0) return 2;
+    if (Cout % 256 == 0) return 1;
+    return 0;
+}
 }  // namespace
 
 DMVAE_API int dmvae_conv_tc_wgrad_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW) {
@@ -1371,6 +1539,8 @@ DMVAE_API int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_m
     g.pix_tiles = B * g.tiles_w * g.tiles_h;
     cudaStream_t st = (cudaStream_t)stream;
     const bool wide_m = Cout >= 256 && g_force_mt != 1;          // two 128-row co tiles per CTA
+    if (const int pmt = wgrad_pair_mt(Cin, Cout))
+        return pmt == 2 ? launch_wgrad_tc2<2>(x, dy, dw_tap_major, g, st) : launch_wgrad_tc2<1>(x, dy, dw_tap_major, g, st);
     if (Cin >= 256) {
         return wide_m ? launch_wgrad_tc<256, 2, 1>(x, dy, dw_tap_major, g, st)
                       : launch_wgrad_tc<256, 1, 1>(x, dy, dw_tap_major, g, st);
@@ -1447,6 +1617,8 @@ DMVAE_API int dmvae_conv_tc_wgrad_strided(const void* x, const void* dy, float* 
     g.pix_tiles = B * g.tiles_w * g.tiles_h;
     cudaStream_t st = (cudaStream_t)stream;
     const bool wide_m = Cout >= 256 && g_force_mt != 1;
+    if (const int pmt = wgrad_pair_mt(Cin, Cout))
+        return pmt == 2 ? launch_wgrad_tc2<2>(x, dy, dw_tap_major, g, st) : launch_wgrad_tc2<1>(x, dy, dw_tap_major, g, st);
     if (Cin >= 256) return wide_m ? launch_wgrad_tc<256, 2, 1>(x, dy, dw_tap_major, g, st) : launch_wgrad_tc<256, 1, 1>(x, dy, dw_tap_major, g, st);
     if (wide_m) return launch_wgrad_tc<128, 2, 2>(x, dy, dw_tap_major, g, st);
     return launch_wgrad_tc<128, 1, 3>(x, dy, dw_tap_major, g, st);
