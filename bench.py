@@ -243,12 +243,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_issue = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+        host_issue["ms"] = (time.perf_counter() - t0) * 1e3 / steps      # host time to ISSUE a step (no device wait)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -263,6 +267,7 @@ def run_ours(args):
         sampler.start()
     _lib.Stats.reset()
     ms = timed(lambda i: tr.step(resident[i % n_pool]), args.steps)
+    host_issue_ms = host_issue["ms"]
     launches = _lib.Stats.launches
     clocks = sampler.stop() if rank == 0 else None
 
@@ -329,7 +334,7 @@ def run_ours(args):
                    "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; 4 rotating input batches"},
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": B * 3 * res * res * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last.get("loss")},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "gpu_launches": launches, "host_issue_ms_per_step": round(host_issue_ms, 3), "clocks": clocks, "roofline": roof,
         "wgrad": {"achieved_tflops": round(wg[2] / (wg[1] * 1e-3) / 1e12, 1) if wg[1] else None, "launches_per_step": wg[0],
                   "share_of_step": round(wg[1] / max(step_ms_prof, 1e-9), 4)},
         "profiled_step_ms": {"total": round(prof_total_ms, 3), "library_kernels": round(lib_ms, 3)},

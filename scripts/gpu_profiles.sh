@@ -13,11 +13,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c
 fi
 if has conv; then
 # halo-resident CTA-pair tiles (N = 256 and N = 128 instantiations), transposed 128-channel tiles, per-tap pair / single tiles, wgrad
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc2h_kernel" -s 30 -c 3 -o gpurun_out/prof_conv_halo -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc2h_kernel" -s 284 -c 3 -o gpurun_out/prof_conv_halo -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_conv.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tcT_kernel" -s 6 -c 2 -o gpurun_out/prof_conv_t -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tcT_kernel" -s 51 -c 2 -o gpurun_out/prof_conv_t -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline >> gpurun_out/ncu_conv.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc2_kernel|conv_tc_kernel|conv_tc_wgrad" -s 40 -c 6 -o gpurun_out/prof_conv -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_wgrad" -s 100 -c 5 -o gpurun_out/prof_conv -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline >> gpurun_out/ncu_conv.log 2>&1
 fi
 if has loss; then
