@@ -700,7 +700,7 @@ struct CfgT {
     static constexpr int A_SLOT = 43 * 1024;                    // (32+2) x (8+2) px x 128 B = 43520 B
     static constexpr int W_BYTES = BM * BK * 2;                 // one tap's weight tile: 128 co x 64 ci
     static constexpr int SA = 2, SW = 7;
-    static constexpr int SMEM_BYTES = SA * A_SLOT + SW * W_BYTES + 1024 + 512;
+    static constexpr int SMEM_BYTES = SA * A_SLOT + SW * W_BYTES + 1024 + 512 + 8 * 2048;   // + one 2 KB transpose patch per epilogue warp
     static constexpr uint32_t TMEM_COLS = 512;                  // two accumulator buffers of 256 pixel columns
     static constexpr int EPI_WARPS = 8;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
@@ -798,15 +798,19 @@ conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
     } else {
         // ============================== epilogue: lane = channel, register = pixel ==============================
+        // Each warp turns its 32 channels x 32 pixels block around through a private 2 KB shared-memory patch so that global
+        // memory sees 16-byte accesses: 4 lanes cover the 64 contiguous bytes (32 channels) of one pixel.
         const int lg = warp & 3;                       // TMEM lanes [32*lg, 32*lg+32) = channels co0 + 32*lg + lane
         const int half = (warp - 2) >> 2;              // pixel columns [128*half, 128*half+128)
+        bf16* patch = reinterpret_cast<bf16*>(smem_w + C::SW * C::W_BYTES + 512) + (warp - 2) * 1024;
+        const int px_l = lane >> 2, grp = lane & 3;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
             const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
-            const int co = nt * BM + lg * 32 + lane;
-            const float bv = bias ? __ldg(bias + co) : 0.f;
+            const int cw = nt * BM + lg * 32;          // first channel of this warp
+            const float bv = bias ? __ldg(bias + cw + lane) : 0.f;
             const int64_t pix0 = ((int64_t)b * g.H + th * THALO_H) * g.W + tw * HALO_W;
             mbar_wait(&tfull[buf], (it >> 1) & 1);
             tc_fence_after();
@@ -815,14 +819,26 @@ conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int c0 = 0; c0 < 128; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) patch[j * 32 + lane] = __float2bfloat16_rn(__uint_as_float(v[j]) + bv);
+                __syncwarp();
                 const int n0 = half * 128 + c0;        // 32 pixel columns = 4 image rows of 8 pixels
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int64_t idx = (pix0 + (int64_t)((n0 + j) >> 3) * g.W + ((n0 + j) & 7)) * g.Cout + co;
-                    float f = __uint_as_float(v[j]) + bv;
-                    if (res) f = bf16_round(f) + __bfloat162float(res[idx]);
-                    out[idx] = __float2bfloat16_rn(f);
+                for (int q = 0; q < 4; ++q) {
+                    const int n = n0 + q * 8 + px_l;
+                    const int64_t idx = (pix0 + (int64_t)(n >> 3) * g.W + (n & 7)) * g.Cout + cw + grp * 8;
+                    uint4 pk = *reinterpret_cast<const uint4*>(patch + (q * 8 + px_l) * 32 + grp * 8);
+                    if (res) {
+                        float f[8], fr[8];
+                        unpack_bf16x8(pk, f);
+                        unpack_bf16x8(*reinterpret_cast<const uint4*>(res + idx), fr);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] += fr[e];               // bf16 conv output + bf16 residual, one rounding
+                        pk = pack_bf16x8(f);
+                    }
+                    *reinterpret_cast<uint4*>(out + idx) = pk;
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
