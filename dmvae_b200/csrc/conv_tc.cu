@@ -181,6 +181,45 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int n, i
     }
 }
 
+// Same as epilogue_chunk for full 32-channel chunks, with the residual values already in registers (prefetched by the caller
+// while the tile's main loop was still running / while the previous chunk was being stored).
+__device__ __forceinline__ void epilogue_chunk_pre(const uint32_t (&v)[32], int n, int64_t pix, const float* __restrict__ bias,
+                                                   const uint4 (&rv)[4], bool has_res, bf16* __restrict__ out, int Cout,
+                                                   double* __restrict__ st, int cpg, int lane) {
+    bf16* op = out + pix * Cout + n;
+    float r[32];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
+        if (has_res) {
+            float fr[8];
+            unpack_bf16x8(rv[q], fr);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];
+        }
+        const uint4 pk = pack_bf16x8(f);
+        *reinterpret_cast<uint4*>(op + q * 8) = pk;
+        if (st) {
+            float fo[8];
+            unpack_bf16x8(pk, fo);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r[q * 8 + e] = fo[e];
+        }
+    }
+    if (st) {
+        switch (cpg) {
+            case 1: chunk_group_stats<1>(r, st, n, lane); break;
+            case 2: chunk_group_stats<2>(r, st, n / 2, lane); break;
+            case 4: chunk_group_stats<4>(r, st, n / 4, lane); break;
+            case 8: chunk_group_stats<8>(r, st, n / 8, lane); break;
+            case 16: chunk_group_stats<16>(r, st, n / 16, lane); break;
+            default: chunk_group_stats<32>(r, st, n / cpg, lane); break;
+        }
+    }
+}
+
 struct TcGeom {
     int B, H, W, Cin, Cout, KH, KW, pt, pl;      // H, W: OUTPUT image size (tiles live on the output grid)
     int stride, IH, IW;                          // conv stride and INPUT image size (IH = H, IW = W when stride == 1)
@@ -663,14 +702,27 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
             const int64_t pix = ((int64_t)b * g.H + th * HALO_H + dh) * g.W + tw * HALO_W + dw;
             const int n0 = nt * BN;
+            // residual: first chunk fetched while the main loop still runs, then one chunk ahead of the stores
+            const bf16* rp = res ? res + pix * g.Cout + n0 : nullptr;
+            uint4 rv[4], rn[4];
+            if (rp) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rv[q] = ld_stream16(rp + q * 8);
+            }
             mbar_wait(&tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (rp && c0 + 32 < BN) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) rn[q] = ld_stream16(rp + c0 + 32 + q * 8);
+                }
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
-                epilogue_chunk(v, n0 + c0, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
+                epilogue_chunk_pre(v, n0 + c0, pix, bias, rv, rp != nullptr, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rv[q] = rn[q];
             }
             tc_fence_before();
             __syncwarp();
@@ -812,10 +864,19 @@ conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const int cw = nt * BM + lg * 32;          // first channel of this warp
             const float bv = bias ? __ldg(bias + cw + lane) : 0.f;
             const int64_t pix0 = ((int64_t)b * g.H + th * THALO_H) * g.W + tw * HALO_W;
+            // the residual tile is fetched while the main loop of this tile is still running (the warp would only wait)
+            uint4 rv[16];
+            if (res) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int n = half * 128 + i * 8 + px_l;
+                    rv[i] = ld_stream16(res + (pix0 + (int64_t)(n >> 3) * g.W + (n & 7)) * g.Cout + cw + grp * 8);
+                }
+            }
             mbar_wait(&tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * 256 + half * 128;
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < 128; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
@@ -831,7 +892,7 @@ conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     if (res) {
                         float f[8], fr[8];
                         unpack_bf16x8(pk, f);
-                        unpack_bf16x8(*reinterpret_cast<const uint4*>(res + idx), fr);
+                        unpack_bf16x8(rv[(c0 >> 3) + q], fr);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] += fr[e];               // bf16 conv output + bf16 residual, one rounding
                         pk = pack_bf16x8(f);

@@ -99,6 +99,10 @@ def main():
                 _lib.query("dmvae_conv_tc_set_tile_mode", 8)
                 us = timeit(lambda i: ops.conv_forward_raw(x, wf, bias, None, k, k, 1, (1, 1)), a.iters, 1)
                 res["fwd_halo_tflops"] = round(flops / us / 1e6, 1)
+                rsd = torch.randn(B, hw, hw, cout, device=DEV).bfloat16()
+                us = timeit(lambda i: ops.conv_forward_raw(x, wf, bias, rsd, k, k, 1, (1, 1)), a.iters, 1)
+                res["fwd_halo_res_tflops"] = round(flops / us / 1e6, 1)
+                del rsd
                 _lib.query("dmvae_conv_tc_set_tile_mode", 7)
             us = timeit(lambda i: ops.conv_wgrad_raw(x, dy, k, k, 1, ((k - 1) // 2, (k - 1) // 2)), a.iters, 1)
             res["wgrad_tflops"] = round(flops / us / 1e6, 1)
