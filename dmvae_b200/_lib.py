@@ -54,6 +54,8 @@ SIGNATURES = {
     "dmvae_nchw_to_nhwc": [_p, _p, _i64, _i, _i64, _i, _p],
     "dmvae_nhwc_to_nchw": [_p, _p, _i64, _i, _i64, _i, _p],
     "dmvae_add_bf16": [_p, _p, _p, _i64, _p],
+    "dmvae_scale_residual": [_p, _p, _p, _i64, _i, _p],
+    "dmvae_layernorm_bf16": [_p, _p, _p, _p, _i64, _i, _f, _p],
     "dmvae_grad_sumsq": [_p, _p, _i64, _p],
     "dmvae_adamw_ema_step": [_p, _p, _p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _f, _p],
 }

@@ -195,6 +195,100 @@ DMVAE_API int dmvae_add_bf16(const void* a, const void* b, void* out, int64_t n,
     return DMVAE_OK;
 }
 
+// ---- frozen-encoder glue (models/vae.py:34-53: the timm ViT under autocast, no_grad) ---------------------------------
+// LayerScale + residual:  x[r][d] += float(y[r][d]) * gamma[d]   (x fp32 residual stream, y the bf16 Linear output).
+// The reference does this as two ATen passes (a type-promoting multiply, then an add); product and sum are rounded
+// separately here too (no FMA contraction), so the result is bit-identical.
+__global__ void __launch_bounds__(256) scale_residual_kernel(float* __restrict__ x, const bf16* __restrict__ y,
+                                                             const float* __restrict__ gamma, int64_t rows, int D) {
+    const int vd = D >> 3;
+    const int64_t nv = rows * vd;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const int c = (int)(i % vd) * 8;
+        float fy[8];
+        unpack_bf16x8(ld_stream16(y + 8 * i), fy);
+        float4 a = *reinterpret_cast<const float4*>(x + 8 * i), b = *reinterpret_cast<const float4*>(x + 8 * i + 4);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        a.x = __fadd_rn(a.x, __fmul_rn(fy[0], g0.x)); a.y = __fadd_rn(a.y, __fmul_rn(fy[1], g0.y));
+        a.z = __fadd_rn(a.z, __fmul_rn(fy[2], g0.z)); a.w = __fadd_rn(a.w, __fmul_rn(fy[3], g0.w));
+        b.x = __fadd_rn(b.x, __fmul_rn(fy[4], g1.x)); b.y = __fadd_rn(b.y, __fmul_rn(fy[5], g1.y));
+        b.z = __fadd_rn(b.z, __fmul_rn(fy[6], g1.z)); b.w = __fadd_rn(b.w, __fmul_rn(fy[7], g1.w));
+        *reinterpret_cast<float4*>(x + 8 * i) = a;
+        *reinterpret_cast<float4*>(x + 8 * i + 4) = b;
+    }
+}
+
+DMVAE_API int dmvae_scale_residual(float* x, const void* y, const float* gamma, int64_t rows, int D, void* stream) {
+    DMVAE_CHECK_ARG(x && y && gamma, "scale_residual: null pointer");
+    DMVAE_CHECK_ARG(rows >= 0 && D > 0 && D % 8 == 0, "scale_residual: need rows >= 0 and D a positive multiple of 8");
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)gamma & 15) == 0, "scale_residual: buffers must be 16-byte aligned");
+    if (rows == 0) return DMVAE_OK;
+    scale_residual_kernel<<<ew_grid(rows * (D / 8)), 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)y, gamma, rows, D);
+    DMVAE_CHECK_LAUNCH("scale_residual_kernel");
+    return DMVAE_OK;
+}
+
+// LayerNorm over the last dimension of an fp32 [rows][D] tensor, output bf16 (what autocast hands the following Linear:
+// layer_norm runs in fp32, the Linear casts its input to bf16).  One warp per row, two passes over registers
+// (mean, then centred variance), D <= 2048.
+template <int VPL>      // float4 vectors per lane: D = 128 * VPL
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ b, bf16* __restrict__ y, int64_t rows, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    constexpr int D = 128 * VPL;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { v[i] = xr[lane + 32 * i]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    s = warp_sum(s);
+    const float mean = s * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + c * c) + (d * d + e * e);
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q * (1.f / D) + eps);
+    bf16* yr = y + row * D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(w + c)), be = __ldg(reinterpret_cast<const float4*>(b + c));
+        const float o0 = (v[i].x - mean) * rstd * g.x + be.x, o1 = (v[i].y - mean) * rstd * g.y + be.y;
+        const float o2 = (v[i].z - mean) * rstd * g.z + be.z, o3 = (v[i].w - mean) * rstd * g.w + be.w;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(yr + c) = pk;
+    }
+}
+
+DMVAE_API int dmvae_layernorm_bf16(const float* x, const float* weight, const float* bias, void* y, int64_t rows, int D, float eps, void* stream) {
+    DMVAE_CHECK_ARG(x && weight && bias && y, "layernorm_bf16: null pointer");
+    DMVAE_CHECK_ARG(rows >= 0, "layernorm_bf16: negative size");
+    DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 7) == 0 && ((uintptr_t)weight & 15) == 0 && ((uintptr_t)bias & 15) == 0,
+                    "layernorm_bf16: buffers must be 16-byte aligned");
+    if (D != 768 && D != 1024 && D != 384 && D != 512)
+        return dmvae_set_error(DMVAE_EUNSUPPORTED, "layernorm_bf16: D=%d not supported (384, 512, 768, 1024)", D);
+    if (rows == 0) return DMVAE_OK;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    bf16* yp = (bf16*)y;
+    switch (D) {
+        case 384: layernorm_bf16_kernel<3><<<grid, 256, 0, st>>>(x, weight, bias, yp, rows, eps); break;
+        case 512: layernorm_bf16_kernel<4><<<grid, 256, 0, st>>>(x, weight, bias, yp, rows, eps); break;
+        case 768: layernorm_bf16_kernel<6><<<grid, 256, 0, st>>>(x, weight, bias, yp, rows, eps); break;
+        default: layernorm_bf16_kernel<8><<<grid, 256, 0, st>>>(x, weight, bias, yp, rows, eps); break;
+    }
+    DMVAE_CHECK_LAUNCH("layernorm_bf16_kernel");
+    return DMVAE_OK;
+}
+
 // ---- weight packing ------------------------------------------------------------------------------------------
 // w[co][ci][kh][kw] fp32  ->  wf[tap][co][ci] bf16  (forward operand, K = ci contiguous)
 //                         ->  wd[tap'][ci][co] bf16 (dgrad operand: tap' = flipped tap, K = co contiguous)

@@ -16,6 +16,7 @@ from contextlib import nullcontext
 import torch
 from torch import nn
 
+from ._lib import call, ptr
 from .autoencoder import Decoder
 
 _VIT = {"base": dict(dim=768, depth=12, heads=12), "large": dict(dim=1024, depth=24, heads=16)}
@@ -124,6 +125,27 @@ class _Gamma(nn.Module):
         return x * self.gamma
 
 
+def _fused_glue_ok(x: torch.Tensor, dim: int) -> bool:
+    """The no-grad encoder pass of stage 1 (train_tokenizer.py:295-297, vae.py:92-93) under autocast(bf16) on a GPU: LayerNorm ->
+    bf16 and LayerScale + residual run as one library kernel each instead of two / two ATen passes."""
+    return (x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.float32 and x.is_contiguous()
+            and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16 and dim in (384, 512, 768, 1024))
+
+
+def _ln_bf16(norm: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    call("dmvae_layernorm_bf16", ptr(x), ptr(norm.weight), ptr(norm.bias), ptr(y), x.numel() // x.shape[-1], x.shape[-1], float(norm.eps))
+    return y
+
+
+def _scale_residual_(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+    """x += y * gamma in place (x: fp32 residual stream owned by the encoder pass, y: bf16 branch output)."""
+    if y.dtype != torch.bfloat16 or not y.is_contiguous():
+        return x.add_(y * gamma)
+    call("dmvae_scale_residual", ptr(x), ptr(y), ptr(gamma), x.numel() // x.shape[-1], x.shape[-1])
+    return x
+
+
 class _Block(nn.Module):
     def __init__(self, dim, heads):
         super().__init__()
@@ -134,7 +156,12 @@ class _Block(nn.Module):
         self.mlp = _Mlp(dim, 4 * dim)
         self.ls2 = _Gamma(dim)
 
-    def forward(self, x):
+    def forward(self, x, own_buffer: bool = False):
+        if _fused_glue_ok(x, x.shape[-1]):
+            if not own_buffer:
+                x = x.clone()                       # the residual stream is updated in place below
+            x = _scale_residual_(x, self.attn(_ln_bf16(self.norm1, x)), self.ls1.gamma)
+            return _scale_residual_(x, self.mlp(_ln_bf16(self.norm2, x)), self.ls2.gamma)
         x = x + self.ls1(self.attn(self.norm1(x)))
         return x + self.ls2(self.mlp(self.norm2(x)))
 
@@ -155,7 +182,9 @@ class DinoViT(nn.Module):
     def forward_features(self, x):
         x = self.patch_embed(x)
         x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embed
-        return self.norm(self.blocks(x))
+        for blk in self.blocks:                     # x is a fresh tensor owned by this pass
+            x = blk(x, own_buffer=True)
+        return self.norm(x)
 
 
 class DINOEncoder(nn.Module):

@@ -176,6 +176,16 @@ int dmvae_nhwc_to_nchw(const void* src, void* dst, int64_t B, int C, int64_t HW,
 /* out = a + b (bf16, fp32 add, one rounding): gradient fan-in of the residual branches (:52, :82). */
 int dmvae_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------ A6: frozen-encoder glue ------------------ */
+/* The timm ViT of models/vae.py:34-53 under autocast + no_grad (train_tokenizer.py:295-297 freezes it): each block computes
+ * x = x + ls(attn(norm1(x))); x = x + ls(mlp(norm2(x))) with an fp32 residual stream and bf16 Linear outputs.
+ * dmvae_scale_residual: x[r][d] += float(y[r][d]) * gamma[d] -- LayerScale multiply + residual add in one pass, each rounded
+ *   separately as the reference's two ATen kernels do (bit-identical).
+ * dmvae_layernorm_bf16: LayerNorm(eps) over the last dim of fp32 x, written as bf16 (autocast runs layer_norm in fp32 and the
+ *   next Linear casts its input to bf16). */
+int dmvae_scale_residual(float* x, const void* y_bf16, const float* gamma, int64_t rows, int D, void* stream);
+int dmvae_layernorm_bf16(const float* x, const float* weight, const float* bias, void* y_bf16, int64_t rows, int D, float eps, void* stream);
+
 /* ------------------------------------------------------------------ N2: fused optimizer step ---------------- */
 /* Replaces clip_grad_norm_ + AdamW.step + update_ema (train_tokenizer.py:140-150,415-417,437; train_dmd.py:540-544) on
  * flat fp32 arenas: sumsq[0] += sum g^2 ; then g *= min(1, max_norm/(||g||+1e-6)), AdamW (torch semantics), EMA. */

@@ -421,3 +421,38 @@ def test_conv_tc_many_tiles_matches_direct():
     dw_tc = ops.conv_wgrad_raw(x, dy, 3, 3)
     dw_d = ops.conv_wgrad_raw(x, dy, 3, 3, force_direct=True)
     assert rel_err(dw_tc, dw_d) < 1e-3
+
+
+def test_vit_glue_scale_residual_bit_exact():
+    """x += float(y) * gamma must equal the reference's two ATen passes (x + y * gamma with type promotion) bit for bit."""
+    from dmvae_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(3)
+    rows, D = 16 * 257, 1024
+    x = torch.randn(rows, D, generator=g, device=DEV)
+    y = torch.randn(rows, D, generator=g, device=DEV).bfloat16()
+    gamma = torch.randn(D, generator=g, device=DEV) * 0.1
+    ref = x + y * gamma
+    out = x.clone()
+    _lib.call("dmvae_scale_residual", _lib.ptr(out), _lib.ptr(y), _lib.ptr(gamma), rows, D)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("D", [384, 768, 1024])
+def test_vit_glue_layernorm_bf16(D):
+    """fp32 LayerNorm written as bf16 vs F.layer_norm(...).to(bf16): same fp32 value up to reassociation, so at most one bf16
+    ulp apart and almost everywhere identical."""
+    from dmvae_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(D)
+    rows = 4112
+    x = torch.randn(rows, D, generator=g, device=DEV) * 2 + 0.3
+    w = torch.rand(D, generator=g, device=DEV) + 0.5
+    b = torch.randn(D, generator=g, device=DEV) * 0.1
+    ref = F.layer_norm(x, (D,), w, b, 1e-6)
+    y = torch.empty(rows, D, dtype=torch.bfloat16, device=DEV)
+    _lib.call("dmvae_layernorm_bf16", _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), rows, D, 1e-6)
+    torch.cuda.synchronize()
+    d = (y.float() - ref.to(torch.bfloat16).float()).abs()
+    assert (d <= ref.abs() * 2 ** -7 + 1e-6).all(), d.max()
+    assert (d > 0).float().mean() < 1e-3
+    assert rel_err(y.float(), ref) < 3e-3            # bf16 rounding of the output itself

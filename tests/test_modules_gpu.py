@@ -393,3 +393,21 @@ def test_dmd_stage_iteration_with_lightningdit():
     assert not torch.equal(vae.encoder.model.blocks[0].attn.qkv.weight, e0)    # encoder is trainable in the DMD stage (:519)
     log2 = tr.step(x, y, vae_turn=False)
     assert "diffusion_loss" in log2 and "dmd_loss" not in log2
+
+
+def test_frozen_encoder_fused_glue_matches_stock_path():
+    """DINOEncoder under no_grad + autocast (stage 1) runs LayerNorm->bf16 and LayerScale+residual as library kernels; the same
+    weights through the stock ATen path (grad mode on) must give the same tokens."""
+    from dmvae_b200.vae import DINOEncoder
+    torch.manual_seed(1)
+    enc = DINOEncoder("base").to(DEV).eval()
+    for blk in enc.model.blocks:                      # LayerScale at its 1e-5 init would hide the branches entirely
+        torch.nn.init.normal_(blk.ls1.gamma, std=0.2)
+        torch.nn.init.normal_(blk.ls2.gamma, std=0.2)
+    x = torch.rand(2, 3, 256, 256, device=DEV) * 2 - 1
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.no_grad():
+            fused = enc(x)
+        stock = enc(x)                                # grad mode on -> ATen ops
+    assert fused.shape == stock.shape == (2, 256, 768)
+    assert rel(fused.float(), stock.float().detach()) < 2e-3
