@@ -293,9 +293,16 @@ def run_ours(args):
     _lib.Stats.timing = False
     prof_total_ms = pe0.elapsed_time(pe1)
     per = {}
+    dump = []
     for name, a, b, work in _lib.Stats.events:
         d = per.setdefault(name, [0, 0.0, 0.0])
-        d[0] += 1; d[1] += a.elapsed_time(b); d[2] += work
+        t = a.elapsed_time(b)
+        d[0] += 1; d[1] += t; d[2] += work
+        dump.append((name, t, work))
+    if os.environ.get("BENCH_DUMP_LAUNCHES") and rank == 0:     # per-launch (entry point, ms, algorithmic flops) of the profiled step
+        with open(os.environ["BENCH_DUMP_LAUNCHES"], "w") as f:
+            json.dump([{"name": n, "ms": round(t, 4), "work": w, "args": list(_lib.Stats.args_log[i]) if i < len(_lib.Stats.args_log) else None}
+                       for i, (n, t, w) in enumerate(dump)], f)
     step_ms_prof = prof_total_ms          # whole profiled step on the device (library kernels + the PyTorch ones)
     lib_ms = sum(v[1] for v in per.values())
 

@@ -115,12 +115,14 @@ class Stats:
     launches = 0
     timing = False
     events = []          # (name, start_event, end_event, work) ; work = algorithmic flops or bytes, see bench.py
+    args_log = []        # integer arguments of each timed call (shapes), parallel to ``events``
     work_fn = None       # callable(name, args) -> float
 
     @classmethod
     def reset(cls):
         cls.launches = 0
         cls.events = []
+        cls.args_log = []
 
 
 def call(name: str, *args) -> None:
@@ -140,6 +142,7 @@ def call(name: str, *args) -> None:
         rc = getattr(lib, name)(*args, _stream())
         e1.record()
         Stats.events.append((name, e0, e1, Stats.work_fn(name, args) if Stats.work_fn else 0.0))
+        Stats.args_log.append(tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 20)))
     else:
         rc = getattr(lib, name)(*args, _stream())
     if rc != 0:

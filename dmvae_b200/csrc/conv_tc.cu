@@ -142,25 +142,37 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int n, i
     const bf16* rp = res ? res + pix * Cout + n : nullptr;
     if (n + 32 <= Cout && (Cout & 7) == 0) {
         float r[32];
+        // rows 32-byte aligned: 256-bit accesses (one full sector per thread instead of two half-sector requests)
+        const bool wide = (Cout & 15) == 0 && (((uintptr_t)out | (uintptr_t)res) & 31) == 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
+        for (int h = 0; h < 2; ++h) {
+            uint4 pk[2], rr[2];
             if (rp) {
-                float fr[8];
-                unpack_bf16x8(*reinterpret_cast<const uint4*>(rp + q * 8), fr);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];   // bf16 conv output, then bf16 add
+                if (wide) ld_stream32(rp + h * 16, rr[0], rr[1]);
+                else { rr[0] = *reinterpret_cast<const uint4*>(rp + h * 16); rr[1] = *reinterpret_cast<const uint4*>(rp + h * 16 + 8); }
             }
-            const uint4 pk = pack_bf16x8(f);
-            *reinterpret_cast<uint4*>(op + q * 8) = pk;
-            if (st) {
-                float fo[8];
-                unpack_bf16x8(pk, fo);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) r[q * 8 + e] = fo[e];
+            for (int qq = 0; qq < 2; ++qq) {
+                const int q = h * 2 + qq;
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
+                if (rp) {
+                    float fr[8];
+                    unpack_bf16x8(rr[qq], fr);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];   // bf16 conv output, then bf16 add
+                }
+                pk[qq] = pack_bf16x8(f);
+                if (st) {
+                    float fo[8];
+                    unpack_bf16x8(pk[qq], fo);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) r[q * 8 + e] = fo[e];
+                }
             }
+            if (wide) st_global32(op + h * 16, pk[0], pk[1]);
+            else { *reinterpret_cast<uint4*>(op + h * 16) = pk[0]; *reinterpret_cast<uint4*>(op + h * 16 + 8) = pk[1]; }
         }
         if (st) {
             switch (cpg) {
@@ -188,25 +200,32 @@ __device__ __forceinline__ void epilogue_chunk_pre(const uint32_t (&v)[32], int 
                                                    double* __restrict__ st, int cpg, int lane) {
     bf16* op = out + pix * Cout + n;
     float r[32];
+    const bool wide = (Cout & 15) == 0 && ((uintptr_t)out & 31) == 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float f[8];
+    for (int h = 0; h < 2; ++h) {
+        uint4 pk[2];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
-        if (has_res) {
-            float fr[8];
-            unpack_bf16x8(rv[q], fr);
+        for (int qq = 0; qq < 2; ++qq) {
+            const int q = h * 2 + qq;
+            float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
+            if (has_res) {
+                float fr[8];
+                unpack_bf16x8(rv[q], fr);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];
+            }
+            pk[qq] = pack_bf16x8(f);
+            if (st) {
+                float fo[8];
+                unpack_bf16x8(pk[qq], fo);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[q * 8 + e] = fo[e];
+            }
         }
-        const uint4 pk = pack_bf16x8(f);
-        *reinterpret_cast<uint4*>(op + q * 8) = pk;
-        if (st) {
-            float fo[8];
-            unpack_bf16x8(pk, fo);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) r[q * 8 + e] = fo[e];
-        }
+        if (wide) st_global32(op + h * 16, pk[0], pk[1]);
+        else { *reinterpret_cast<uint4*>(op + h * 16) = pk[0]; *reinterpret_cast<uint4*>(op + h * 16 + 8) = pk[1]; }
     }
     if (st) {
         switch (cpg) {
@@ -707,7 +726,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint4 rv[4], rn[4];
             if (rp) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) rv[q] = ld_stream16(rp + q * 8);
+                for (int q = 0; q < 4; q += 2) ld_stream32(rp + q * 8, rv[q], rv[q + 1]);     // Cout % 128 == 0 here: 32-byte aligned
             }
             mbar_wait(&tfull[buf], (it >> 1) & 1);
             tc_fence_after();
@@ -716,7 +735,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (rp && c0 + 32 < BN) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) rn[q] = ld_stream16(rp + c0 + 32 + q * 8);
+                    for (int q = 0; q < 4; q += 2) ld_stream32(rp + c0 + 32 + q * 8, rn[q], rn[q + 1]);
                 }
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
@@ -1477,7 +1496,8 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
             return launch_conv_tcT(x, w_packed, bias, residual, y, gt, st);
     }
     // halo-resident CTA pairs: 3x3 filters, 16 x 8 pixel tiles, full N tiles, at least ~3/8 of a wave of pair tiles
-    if (g_halo && (g_force_mt == 0 || g_halo == 2) && KH == 3 && KW == 3 && bn >= 128 && Cout % bn == 0 && Cin % BK == 0 && W % HALO_W == 0 && H % HALO_H == 0) {
+    if (g_halo && (g_force_mt == 0 || g_halo == 2) && KH == 3 && KW == 3 && bn >= 128 && Cout % bn == 0 && Cin % BK == 0 && W % HALO_W == 0 && H % HALO_H == 0 &&
+        (((uintptr_t)y | (uintptr_t)residual) & 31) == 0) {
         TcGeom gh = g;
         gh.BW = HALO_W; gh.BH = HALO_H;
         gh.tiles_w = W / HALO_W; gh.tiles_h = H / HALO_H;
