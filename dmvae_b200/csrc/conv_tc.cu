@@ -239,6 +239,66 @@ __device__ __forceinline__ void epilogue_chunk_pre(const uint32_t (&v)[32], int 
     }
 }
 
+// Line-coalesced epilogue for one warp: 32 accumulator rows (pixels) x 64 columns (channels).
+// tcgen05.ld hands every thread ITS pixel's 32 consecutive channels, so direct stores touch 32 different 128-byte lines per
+// instruction (ncu on the 1x1 layers: l1tex 66 % busy, tensor pipe 8 %, 12 k cycles per tile in the epilogue).  Here the block
+// is first written to a 4 KB shared-memory patch (row = one pixel's 128 bytes, 16-byte chunks XOR-swizzled by the row so both
+// directions are conflict-free) and read back so that 8 consecutive lanes cover one pixel's full line: 4 lines per instruction,
+// for the residual loads as well.  The residual block is fetched before the accumulator is read, so its latency is hidden.
+struct EpiGeom {
+    int64_t tile_pix0;     // pixel index of tile row 0
+    int W, bw_shift, bw_mask, Cout;
+};
+__device__ __forceinline__ void epilogue_block64(uint32_t taddr, int n, int row0, const EpiGeom& eg, const float* __restrict__ bias,
+                                                 const bf16* __restrict__ res, bf16* __restrict__ out, uint4* __restrict__ patch, int lane) {
+    const int c = lane & 7, rsub = lane >> 3;
+    int64_t idx[8];
+    uint4 rv[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int rr = row0 + it * 4 + rsub;
+        idx[it] = (eg.tile_pix0 + (int64_t)(rr >> eg.bw_shift) * eg.W + (rr & eg.bw_mask)) * eg.Cout + n + c * 8;
+        if (res) rv[it] = ld_stream16(res + idx[it]);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(taddr + half * 32, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float f[8];
+            if (bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n + half * 32 + q * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + half * 32 + q * 8 + 4));
+                f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
+                f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
+                f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
+                f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+            }
+            patch[lane * 8 + ((half * 4 + q) ^ (lane & 7))] = pack_bf16x8(f);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rsub;
+        uint4 pk = patch[r * 8 + (c ^ (r & 7))];
+        if (res) {
+            float f[8], fr[8];
+            unpack_bf16x8(pk, f);
+            unpack_bf16x8(rv[it], fr);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += fr[e];               // bf16 conv output + bf16 residual, one rounding
+            pk = pack_bf16x8(f);
+        }
+        *reinterpret_cast<uint4*>(out + idx[it]) = pk;
+    }
+    __syncwarp();
+}
+
 struct TcGeom {
     int B, H, W, Cin, Cout, KH, KW, pt, pl;      // H, W: OUTPUT image size (tiles live on the output grid)
     int stride, IH, IW;                          // conv stride and INPUT image size (IH = H, IW = W when stride == 1)
@@ -450,7 +510,7 @@ template <int BN> struct Cfg2 {
     static constexpr int B_BYTES = (BN / 2) * BK * 2;           // this CTA's half of the weight tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * 4096;     // + one 4 KB store patch per epilogue warp
     static constexpr uint32_t TMEM_COLS = 2 * BN;               // two accumulator buffers of BN columns
     static constexpr int THREADS = 192;
 };
@@ -555,13 +615,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_wait(&tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
+            if (!stats && (g.Cout & 63) == 0) {
+                EpiGeom eg;
+                eg.tile_pix0 = ((int64_t)b * g.H + th * g.BH) * g.W + tw * g.BW;
+                eg.W = g.W; eg.bw_shift = 31 - __clz(g.BW); eg.bw_mask = g.BW - 1; eg.Cout = g.Cout;
+                uint4* patch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 256) + (warp - 2) * 256;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                const int n = n0 + c0;
-                if (n >= g.Cout) continue;
-                epilogue_chunk(v, n, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
+                for (int c0 = 0; c0 < BN; c0 += 64) {
+                    if (n0 + c0 >= g.Cout) break;
+                    epilogue_block64(taddr + c0, n0 + c0, lg * 32, eg, bias, res, out, patch, lane);
+                }
+            } else {
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    const int n = n0 + c0;
+                    if (n >= g.Cout) continue;
+                    epilogue_chunk(v, n, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -596,7 +668,7 @@ template <int BN> struct CfgH {
     static constexpr int B_BYTES = (BN / 2) * BK * 2;           // this CTA's half of one tap's weight tile
     static constexpr int SA = BN == 256 ? 3 : 4;
     static constexpr int SB = (200 * 1024 - SA * A_SLOT3) / B_BYTES > 12 ? 12 : (200 * 1024 - SA * A_SLOT3) / B_BYTES;
-    static constexpr int SMEM_BYTES = SA * A_SLOT3 + SB * B_BYTES + 1024 + 512;
+    static constexpr int SMEM_BYTES = SA * A_SLOT3 + SB * B_BYTES + 1024 + 512 + 4 * 4096;   // + one 4 KB store patch per epilogue warp
     static constexpr uint32_t TMEM_COLS = 2 * BN;
     static constexpr int THREADS = 192;
 };
@@ -721,27 +793,40 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
             const int64_t pix = ((int64_t)b * g.H + th * HALO_H + dh) * g.W + tw * HALO_W + dw;
             const int n0 = nt * BN;
-            // residual: first chunk fetched while the main loop still runs, then one chunk ahead of the stores
-            const bf16* rp = res ? res + pix * g.Cout + n0 : nullptr;
-            uint4 rv[4], rn[4];
-            if (rp) {
-#pragma unroll
-                for (int q = 0; q < 4; q += 2) ld_stream32(rp + q * 8, rv[q], rv[q + 1]);     // Cout % 128 == 0 here: 32-byte aligned
-            }
-            mbar_wait(&tfull[buf], (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
+            if (!stats) {
+                // residual rows are fetched (line-coalesced) before the accumulator is ready, see epilogue_block64
+                EpiGeom eg;
+                eg.tile_pix0 = ((int64_t)b * g.H + th * HALO_H) * g.W + tw * HALO_W;
+                eg.W = g.W; eg.bw_shift = 3; eg.bw_mask = HALO_W - 1; eg.Cout = g.Cout;
+                uint4* patch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512) + (warp - 2) * 256;
+                mbar_wait(&tfull[buf], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (rp && c0 + 32 < BN) {
+                for (int c0 = 0; c0 < BN; c0 += 64) epilogue_block64(taddr + c0, n0 + c0, lg * 32, eg, bias, res, out, patch, lane);
+            } else {
+                // fused GroupNorm statistics: per-thread rows (the statistics are reduced per pixel row), residual one chunk ahead
+                const bf16* rp = res ? res + pix * g.Cout + n0 : nullptr;
+                uint4 rv[4], rn[4];
+                if (rp) {
 #pragma unroll
-                    for (int q = 0; q < 4; q += 2) ld_stream32(rp + c0 + 32 + q * 8, rn[q], rn[q + 1]);
+                    for (int q = 0; q < 4; q += 2) ld_stream32(rp + q * 8, rv[q], rv[q + 1]);     // Cout % 128 == 0 here: 32-byte aligned
                 }
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                epilogue_chunk_pre(v, n0 + c0, pix, bias, rv, rp != nullptr, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
+                mbar_wait(&tfull[buf], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    if (rp && c0 + 32 < BN) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) rv[q] = rn[q];
+                        for (int q = 0; q < 4; q += 2) ld_stream32(rp + c0 + 32 + q * 8, rn[q], rn[q + 1]);
+                    }
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    epilogue_chunk_pre(v, n0 + c0, pix, bias, rv, rp != nullptr, out, g.Cout, stats + (int64_t)b * 64, g.cpg, lane);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) rv[q] = rn[q];
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -881,11 +966,12 @@ conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const int mt = tile / g.n_tiles, nt = tile % g.n_tiles;
             const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
             const int cw = nt * BM + lg * 32;          // first channel of this warp
-            const float bv = bias ? __ldg(bias + cw + lane) : 0.f;
+            const bool live = cw < g.Cout;             // Cout = 64: the upper half of the 128-row tile is TMA zero fill, nothing to store
+            const float bv = (bias && live && cw + lane < g.Cout) ? __ldg(bias + cw + lane) : 0.f;
             const int64_t pix0 = ((int64_t)b * g.H + th * THALO_H) * g.W + tw * HALO_W;
             // the residual tile is fetched while the main loop of this tile is still running (the warp would only wait)
             uint4 rv[16];
-            if (res) {
+            if (res && live && (g.Cout & 31) == 0) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int n = half * 128 + i * 8 + px_l;
@@ -895,8 +981,33 @@ conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             mbar_wait(&tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * 256 + half * 128;
+            if (live && (g.Cout & 31) != 0) {
+                // thin output (the 128 -> 3 head, the 64 -> 3 stem gradient): a few live channel lanes, scalar bf16 stores
+                const bool lane_live = cw + lane < g.Cout;
+                const float bs = (bias && lane_live) ? __ldg(bias + cw + lane) : 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    if (lane_live) {
+                        const int n0 = half * 128 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int64_t idx = (pix0 + (int64_t)((n0 + j) >> 3) * g.W + ((n0 + j) & 7)) * g.Cout + cw + lane;
+                            float f = __uint_as_float(v[j]) + bs;
+                            if (res) f = bf16_round(f) + __bfloat162float(res[idx]);
+                            out[idx] = __float2bfloat16_rn(f);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+                continue;
+            }
 #pragma unroll
             for (int c0 = 0; c0 < 128; c0 += 32) {
+                if (!live) break;                      // warp-uniform
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
 #pragma unroll
@@ -1485,13 +1596,13 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     if (g_force_mt == 1) mt = 1;
     if (g_force_mt == 2 && bn >= 128 && pick_pixel_tile_n(H, W, 2 * BM, &bw2, &bh2)) mt = 2;
     // transposed halo tiles for 128-channel outputs (an N = 128 instruction only half-fills the tensor pipe)
-    if (g_halo && (g_force_mt == 0 || g_halo == 2) && KH == 3 && KW == 3 && bn == 128 && Cout % BM == 0 && Cin % BK == 0 && !stats &&
-        W % HALO_W == 0 && H % THALO_H == 0) {
+    if (g_halo && (g_force_mt == 0 || g_halo == 2) && KH == 3 && KW == 3 && ((bn == 128 && Cout % 64 == 0) || (bn == 32 && Cout < 32)) &&
+        Cin % BK == 0 && !stats && W % HALO_W == 0 && H % THALO_H == 0 && (((uintptr_t)y | (uintptr_t)residual) & 15) == 0) {
         TcGeom gt = g;
         gt.BW = HALO_W; gt.BH = THALO_H;
         gt.tiles_w = W / HALO_W; gt.tiles_h = H / THALO_H;
         gt.m_tiles = B * gt.tiles_w * gt.tiles_h;
-        gt.n_tiles = Cout / BM;
+        gt.n_tiles = (Cout + BM - 1) / BM;
         if (g_halo == 2 || gt.m_tiles * gt.n_tiles >= (num_sms() * 3) / 4)
             return launch_conv_tcT(x, w_packed, bias, residual, y, gt, st);
     }

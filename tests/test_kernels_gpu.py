@@ -310,6 +310,10 @@ def test_conv_tcgen05_tile_modes(case, mode):
     (2, 128, 128, 32, 16, 3, 1, (1, 1), True),    # Cout = 128, H % 32 == 0: transposed tile (channels in TMEM lanes), residual
     (1, 256, 128, 64, 24, 3, 1, (1, 1), False),   # transposed tile, 4 chunks, 6 tiles
     (3, 64, 128, 32, 8, 3, 1, (1, 1), True),      # transposed tile, image exactly one tile wide
+    (2, 64, 64, 32, 16, 3, 1, (1, 1), True),      # Cout = 64 (VGG conv1_2): half of the transposed tile is zero fill
+    (1, 128, 192, 32, 16, 3, 1, (1, 1), False),   # Cout = 192: second channel tile half empty
+    (2, 128, 3, 32, 16, 3, 1, (1, 1), False),     # the 128 -> 3 head on the transposed tile (3 live channel lanes)
+    (1, 64, 5, 64, 8, 3, 1, (1, 1), True),        # thin output with a residual
 ])
 def test_conv_tcgen05_halo_tiles(case):
     """Halo-resident CTA-pair tiles (one (16+2) x (8+2) pixel tile serves all nine taps) against the fp32 reference, and
