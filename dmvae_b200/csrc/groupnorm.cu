@@ -26,9 +26,9 @@ static int gn_geom(int C, GnGeom* g, const char* who) {
 }
 
 #include <stdlib.h>
-static int gn_ctas_per_sm() {          // tuning knob (DMVAE_GN_CTAS_PER_SM), default 16 CTAs per SM worth of grid
-    static int v = 0;
-    if (!v) { const char* e = getenv("DMVAE_GN_CTAS_PER_SM"); v = e ? atoi(e) : 16; if (v < 1) v = 16; }
+static int gn_ctas_per_sm() {          // tuning knob (DMVAE_GN_CTAS_PER_SM): grid = 148 x this many CTAs.  4 = two exactly full waves of the
+    static int v = 0;                  // backward kernels (2 resident CTAs per SM); measured best of {3,4,6,8,16} for stats, apply and backward
+    if (!v) { const char* e = getenv("DMVAE_GN_CTAS_PER_SM"); v = e ? atoi(e) : 4; if (v < 1) v = 4; }
     return v;
 }
 static int gn_min_passes() {           // minimum row-passes of work per CTA (amortises the per-CTA coefficient prologue)
@@ -162,8 +162,8 @@ __device__ __forceinline__ float gn_dy(float da, float yv) {
     return da * fmaf(yv * sg, 1.f - sg, sg);
 }
 
-template <bool SILU>
-__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(
+template <bool SILU, int U>
+__global__ void __launch_bounds__(GN_THREADS, U <= 2 ? 3 : 2) gn_bwd_reduce_kernel(
     const bf16* __restrict__ da, const bf16* __restrict__ x, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ gsum,
     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t HW, int C, int vc, int rows, int64_t ppb, float eps) {
@@ -191,7 +191,6 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
     const int64_t off = (int64_t)b * HW * C + col * 8;
-    constexpr int U = 2;
     for (int64_t p = p0 + row; p < p1; p += (int64_t)rows * U) {
         uint4 vx[U], vd[U];
 #pragma unroll
@@ -230,8 +229,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(
     }
 }
 
-template <bool SILU>
-__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
+template <bool SILU, int U>
+__global__ void __launch_bounds__(GN_THREADS, U <= 2 ? 3 : 2) gn_bwd_apply_kernel(
     const bf16* __restrict__ da, const bf16* __restrict__ x, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ gsum,
     const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ colsum, int64_t HW, int C, int vc, int rows,
@@ -263,7 +262,6 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
     const int64_t off = (int64_t)b * HW * C + col * 8;
-    constexpr int U = 2;
     for (int64_t p = p0 + row; p < p1; p += (int64_t)rows * U) {
         uint4 vx[U], vd[U], vr[U];
 #pragma unroll
@@ -359,15 +357,22 @@ DMVAE_API int dmvae_gn_bwd(const void* da, const void* x, const double* stats, c
     const size_t smem = (size_t)4 * C * sizeof(float);
     const size_t smem_r = (size_t)6 * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    static int U = 0;
+    if (!U) { const char* e = getenv("DMVAE_GN_BWD_U"); U = e ? atoi(e) : 4; if (U != 2 && U != 3 && U != 4) U = 4; }     // 16-byte loads in flight per tensor per thread
+#define GN_BWD_LAUNCH(S, UU)                                                                                                              \
+    do {                                                                                                                                  \
+        gn_bwd_reduce_kernel<S, UU><<<grid, GN_THREADS, smem_r, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, \
+                                                                      dbeta, HW, C, g.vc, g.rows, ppb, eps);                              \
+        DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");                                                                                       \
+        gn_bwd_apply_kernel<S, UU><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum,            \
+                                                                   (const bf16*)dres, (bf16*)dx, dx_colsum, HW, C, g.vc, g.rows, ppb, eps); \
+    } while (0)
     if (silu) {
-        gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem_r, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
-        DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");
-        gn_bwd_apply_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, dx_colsum, HW, C, g.vc, g.rows, ppb, eps);
+        if (U == 2) GN_BWD_LAUNCH(true, 2); else if (U == 3) GN_BWD_LAUNCH(true, 3); else GN_BWD_LAUNCH(true, 4);
     } else {
-        gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem_r, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, dgamma, dbeta, HW, C, g.vc, g.rows, ppb, eps);
-        DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");
-        gn_bwd_apply_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum, (const bf16*)dres, (bf16*)dx, dx_colsum, HW, C, g.vc, g.rows, ppb, eps);
+        if (U == 2) GN_BWD_LAUNCH(false, 2); else if (U == 3) GN_BWD_LAUNCH(false, 3); else GN_BWD_LAUNCH(false, 4);
     }
+#undef GN_BWD_LAUNCH
     DMVAE_CHECK_LAUNCH("gn_bwd_apply_kernel");
     return DMVAE_OK;
 }
