@@ -169,7 +169,8 @@ class Stress512Trainer:
             rec = self.dec(z).float()
             l1, _ = self.losses.l1_l2_loss(rec, images)
             loss = l1 + 1e-6 * kl
-        loss.backward()
+        with self.arena.direct():
+            loss.backward()
         self.arena.allreduce()
         return {"loss": loss.detach(), "vae_norm": self.opt.step()}
 

@@ -10,6 +10,8 @@ never written in place -- the adaptive-GAN-weight code of train_dmd.py:248-251 r
 """
 from __future__ import annotations
 
+import contextlib
+
 from typing import Optional, Tuple
 
 import torch
@@ -97,9 +99,45 @@ def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[tor
     return y
 
 
+class _DirectGrads:
+    """While a trainer's ``backward()`` runs inside ``direct_param_grads(arena)``, the custom Functions below accumulate parameter
+    gradients straight into the parameters' slots of the flat gradient arena (the kernels already accumulate: ``red.add`` /
+    ``+=``) and return None to autograd, instead of materialising a gradient tensor that AccumulateGrad then adds into ``.grad``
+    with one more elementwise kernel per parameter (the reference's DDP path does that add too, train_dmd.py:348).  Outside the
+    context -- ``torch.autograd.grad`` on ``conv_out.weight`` (train_dmd.py:249-250), plain ``.backward()`` -- nothing changes."""
+    arena = None
+
+
+@contextlib.contextmanager
+def direct_param_grads(arena):
+    prev, _DirectGrads.arena = _DirectGrads.arena, arena
+    try:
+        yield
+    finally:
+        _DirectGrads.arena = prev
+
+
+def _grad_slot(p) -> Optional[torch.Tensor]:
+    """The arena view to accumulate into, or None when direct mode is off / p is not an arena parameter / p.grad was re-pointed."""
+    a = _DirectGrads.arena
+    if a is None or p is None:
+        return None
+    slot = a.slot_of(p)
+    if slot is None or p.grad is None or p.grad.data_ptr() != slot.data_ptr():
+        return None
+    return slot
+
+
+def _grad_done(p) -> None:
+    a = _DirectGrads.arena
+    if a is not None:
+        a.notify(p)
+
+
 def conv_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, stride: int = 1, pad_tl: Tuple[int, int] = (1, 1),
-                   force_direct: bool = False) -> torch.Tensor:
-    """dw (Cout, Cin, KH, KW) fp32 = sum_pixels dy (x) x."""
+                   force_direct: bool = False, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """dw (Cout, Cin, KH, KW) fp32 = sum_pixels dy (x) x.  With ``out`` (a contiguous fp32 tensor of that shape) the result is
+    ACCUMULATED into it and None is returned."""
     B, H, W, cin = x.shape
     _, OH, OW, cout = dy.shape
     pt, pl = pad_tl
@@ -107,17 +145,26 @@ def conv_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, stride: 
     if same and not force_direct and query("dmvae_conv_tc_wgrad_supported", B, H, W, cin, cout, kh, kw):
         scratch = torch.zeros((kh * kw, cout, cin), dtype=torch.float32, device=x.device)
         call("dmvae_conv_tc_wgrad", ptr(x), ptr(dy), ptr(scratch), B, H, W, cin, cout, kh, kw)
+        if out is not None:
+            call("dmvae_wgrad_unpack", ptr(scratch), ptr(out), cout, cin, kh * kw, 1)
+            return None
         dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
         call("dmvae_wgrad_unpack", ptr(scratch), ptr(dw), cout, cin, kh * kw, 0)
         return dw
     if stride == 2 and not force_direct and query("dmvae_conv_tc_strided_supported", B, H, W, cin, OH, OW, cout, kh, kw, stride):
         scratch = torch.zeros((kh * kw, cout, cin), dtype=torch.float32, device=x.device)
         call("dmvae_conv_tc_wgrad_strided", ptr(x), ptr(dy), ptr(scratch), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
+        if out is not None:
+            call("dmvae_wgrad_unpack", ptr(scratch), ptr(out), cout, cin, kh * kw, 1)
+            return None
         dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
         call("dmvae_wgrad_unpack", ptr(scratch), ptr(dw), cout, cin, kh * kw, 0)
         return dw
     dw = torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
     call("dmvae_conv_direct_wgrad", ptr(x), ptr(dy), ptr(dw), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
+    if out is not None:
+        out.add_(dw)
+        return None
     return dw
 
 
@@ -141,8 +188,12 @@ def conv_dgrad_raw(dy: torch.Tensor, w_fwd: torch.Tensor, w_dgrad: torch.Tensor,
     return dx
 
 
-def bias_grad_raw(dy: torch.Tensor) -> torch.Tensor:
+def bias_grad_raw(dy: torch.Tensor, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Column sums of dy; with ``out`` (fp32 [C]) they are accumulated into it (the kernel adds) and None is returned."""
     c = dy.shape[-1]
+    if out is not None:
+        call("dmvae_bias_grad", ptr(dy), ptr(out), dy.numel() // c, c)
+        return None
     db = torch.zeros((c,), dtype=torch.float32, device=dy.device)
     call("dmvae_bias_grad", ptr(dy), ptr(db), dy.numel() // c, c)
     return db
@@ -169,18 +220,22 @@ def gn_apply_raw(x, stats, gamma, beta, silu: bool, eps: float = GN_EPS) -> torc
     return y
 
 
-def gn_bwd_raw(da, x, stats, gamma, beta, silu: bool, dres=None, eps: float = GN_EPS, want_colsum: bool = False):
+def gn_bwd_raw(da, x, stats, gamma, beta, silu: bool, dres=None, eps: float = GN_EPS, want_colsum: bool = False,
+               out_dgamma: Optional[torch.Tensor] = None, out_dbeta: Optional[torch.Tensor] = None):
+    """Returns (dx, dgamma, dbeta); with ``out_dgamma`` / ``out_dbeta`` (fp32 [C]) the affine gradients are accumulated into them
+    (the kernel adds atomically) and None is returned in their place."""
     B, H, W, c = x.shape
     gsum = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
     # one zero-filled fp32 buffer for dgamma | dbeta | column sums
-    small = torch.zeros((3, c), dtype=torch.float32, device=x.device)
-    dgamma, dbeta, colsum = small[0], small[1], small[2]
+    direct = out_dgamma is not None and out_dbeta is not None
+    small = torch.zeros((1 if direct else 3, c), dtype=torch.float32, device=x.device)
+    dgamma, dbeta, colsum = (out_dgamma, out_dbeta, small[0]) if direct else (small[0], small[1], small[2])
     dx = torch.empty_like(x)
     call("dmvae_gn_bwd", ptr(da), ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(gsum), ptr(dgamma), ptr(dbeta), ptr(dres),
          ptr(dx), ptr(colsum) if want_colsum else None, B, H * W, c, eps, int(silu))
     if want_colsum:
         _tag_colsum(dx, colsum)
-    return dx, dgamma, dbeta
+    return (dx, None, None) if direct else (dx, dgamma, dbeta)
 
 
 def _ver(t: torch.Tensor) -> int:
@@ -247,6 +302,7 @@ class ConvFn(torch.autograd.Function):
         ctx.geom = (kh, kw, stride, pad_tl, x.shape[1:3])
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
+        ctx.params = (weight, bias)                  # for direct accumulation into the gradient arena (see _DirectGrads)
         ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, w_fwd, w_dgrad)
         return y
 
@@ -262,14 +318,36 @@ class ConvFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = conv_dgrad_raw(dy, w_fwd, w_dgrad, in_hw, kh, kw, stride, pad_tl)
             if ctx.needs_input_grad[1]:
-                dw = conv_wgrad_raw(x, dy, kh, kw, stride, pad_tl)
+                slot = _grad_slot(ctx.params[0])
+                dw = conv_wgrad_raw(x, dy, kh, kw, stride, pad_tl, out=slot)
+                if slot is not None:
+                    _grad_done(ctx.params[0])
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _tagged_colsum(dy)                 # already reduced by the kernel that wrote dy (gn_bwd)
             if db is None:
-                db = bias_grad_raw(dy)
+                slot = _grad_slot(ctx.params[1])
+                db = bias_grad_raw(dy, out=slot)
+                if slot is not None:
+                    _grad_done(ctx.params[1])
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
         return dx, dw, db, dres, None, None, None, None, None
+
+
+def _affine_slots(ctx):
+    """Arena slots of a GroupNorm's (gamma, beta) when both can be accumulated directly, else (None, None)."""
+    if not (ctx.needs_input_grad[1] and ctx.needs_input_grad[2]):
+        return None, None
+    sg, sb = _grad_slot(ctx.params[0]), _grad_slot(ctx.params[1])
+    if sg is None or sb is None:
+        return None, None
+    return sg, sb
+
+
+def _affine_done(ctx, sg) -> None:
+    if sg is not None:                      # after the kernel that accumulates into the slots has been enqueued
+        _grad_done(ctx.params[0])
+        _grad_done(ctx.params[1])
 
 
 class GroupNormSiluFn(torch.autograd.Function):
@@ -284,6 +362,7 @@ class GroupNormSiluFn(torch.autograd.Function):
             stats = gn_stats_raw(x)
         y = gn_apply_raw(x, stats, g, b, silu)
         ctx.silu = silu
+        ctx.params = (gamma, beta)
         ctx.save_for_backward(x, stats, g, b)
         return y
 
@@ -291,7 +370,9 @@ class GroupNormSiluFn(torch.autograd.Function):
     def backward(ctx, da):
         x, stats, g, b = ctx.saved_tensors
         da = _chk_nhwc(da, "group_norm backward")
-        dx, dgamma, dbeta = gn_bwd_raw(da, x, stats, g, b, ctx.silu, want_colsum=True)
+        sg, sb = _affine_slots(ctx)
+        dx, dgamma, dbeta = gn_bwd_raw(da, x, stats, g, b, ctx.silu, want_colsum=True, out_dgamma=sg, out_dbeta=sb)
+        _affine_done(ctx, sg)
         return dx, dgamma, dbeta, None
 
 
@@ -309,6 +390,7 @@ class GroupNormSiluSkipFn(torch.autograd.Function):
             stats = gn_stats_raw(x)
         y = gn_apply_raw(x, stats, g, b, silu)
         ctx.silu = silu
+        ctx.params = (gamma, beta)
         ctx.save_for_backward(x, stats, g, b)
         return y, x.view_as(x)
 
@@ -319,7 +401,9 @@ class GroupNormSiluSkipFn(torch.autograd.Function):
             return dskip, None, None, None
         da = _chk_nhwc(da, "group_norm backward")
         dres = None if dskip is None else _chk_nhwc(dskip, "group_norm skip gradient")
-        dx, dgamma, dbeta = gn_bwd_raw(da, x, stats, g, b, ctx.silu, dres=dres, want_colsum=True)
+        sg, sb = _affine_slots(ctx)
+        dx, dgamma, dbeta = gn_bwd_raw(da, x, stats, g, b, ctx.silu, dres=dres, want_colsum=True, out_dgamma=sg, out_dbeta=sb)
+        _affine_done(ctx, sg)
         return dx, dgamma, dbeta, None
 
 

@@ -147,7 +147,8 @@ class TokenizerTrainer:
         with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
             recon = self.vae(images, freeze_encoder=True)
             loss, log = self.loss_fn.forward_generator(images, recon)
-        loss.backward()
+        with self.arena.direct():                   # conv / GroupNorm gradients accumulate straight into the arena
+            loss.backward()
         self.arena.allreduce()
         if self.fused is not None:                  # clip + AdamW + EMA in two kernels over the flat arenas
             log["vae_norm"] = self.fused.step()
@@ -214,7 +215,8 @@ class DmdTrainer:
                     p.requires_grad = False
                 loss, log = self.loss_fn.forward_generator(images, recon, latents, labels, compute_dmd=self.cfg.dmd_weight > 0)
         if vae_turn:
-            loss.backward()
+            with self.arena_vae.direct():
+                loss.backward()
             self.arena_vae.allreduce()
             log["vae_norm"] = self._clip_step(self.arena_vae, self.opt_vae)
             log["loss"] = loss.detach()

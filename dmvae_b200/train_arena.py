@@ -37,6 +37,8 @@ class GradArena:
         self._pending = list(self.members)
         self._handles: List = []
         self._launched = [False] * len(self.bounds)
+        self._slots: Dict[int, torch.Tensor] = {}
+        self.overlap = False
         self._attach()
         self.overlap = overlap and self._distributed()
         if self.overlap:
@@ -52,7 +54,23 @@ class GradArena:
         for p in self.params:      # (re-)attach in case an optimizer dropped the views (set_to_none)
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self._slots[id(p)] = p.grad
             off += p.numel()
+
+    def slot_of(self, p):
+        """The arena view that is ``p.grad`` (None for tensors this arena does not own)."""
+        return self._slots.get(id(p))
+
+    def notify(self, p: nn.Parameter):
+        """A custom Function accumulated p's gradient straight into its slot (ops.direct_param_grads): what the
+        post-accumulate-grad hook would have reported."""
+        if self.overlap:
+            self._on_grad_ready(p)
+
+    def direct(self):
+        """Context manager for ``loss.backward()``: dmvae_b200 ops write parameter gradients directly into this arena."""
+        from . import ops
+        return ops.direct_param_grads(self)
 
     def zero(self):
         self.flat.zero_()
