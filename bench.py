@@ -350,7 +350,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline and args.workload == "tokenizer":
         out["cpu_baseline"] = cpu_step_baseline(sample_images=1, reps=1)
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -417,7 +417,7 @@ def run_reference(args):
         loss = st.step(xs[i % 2])
     dt = time.perf_counter() - t0
     v = round(b * args.steps / dt, 4)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -427,10 +427,31 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps of {b} image(s) after {args.warmup} warm-up"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "last_loss": loss}), flush=True)
+        "gpu_launches": 0, "last_loss": loss})
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line, the result JSON: NCCL (version banner), cuDNN and anything else that writes to fd 1 is
+    sent to stderr for the rest of the process; emit() writes the line to the real stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
