@@ -249,17 +249,24 @@ struct EpiGeom {
     int64_t tile_pix0;     // pixel index of tile row 0
     int W, bw_shift, bw_mask, Cout;
 };
-__device__ __forceinline__ void epilogue_block64(uint32_t taddr, int n, int row0, const EpiGeom& eg, const float* __restrict__ bias,
-                                                 const bf16* __restrict__ res, bf16* __restrict__ out, uint4* __restrict__ patch, int lane) {
-    const int c = lane & 7, rsub = lane >> 3;
-    int64_t idx[8];
-    uint4 rv[8];
+// row offsets (elements, relative to tile_pix0 * Cout) of the 8 pixel rows this lane touches in the read-back phase
+__device__ __forceinline__ void epilogue_row_offsets(int row0, const EpiGeom& eg, int lane, int (&off)[8]) {
+    const int rsub = lane >> 3;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int rr = row0 + it * 4 + rsub;
-        idx[it] = (eg.tile_pix0 + (int64_t)(rr >> eg.bw_shift) * eg.W + (rr & eg.bw_mask)) * eg.Cout + n + c * 8;
-        if (res) rv[it] = ld_stream16(res + idx[it]);
+        off[it] = ((rr >> eg.bw_shift) * eg.W + (rr & eg.bw_mask)) * eg.Cout + (lane & 7) * 8;
     }
+}
+// the residual values of one 32-row x 64-channel block, line-coalesced (8 lanes = one pixel's 128 bytes)
+__device__ __forceinline__ void epilogue_load_residual(const bf16* __restrict__ res_tile, int n, const int (&off)[8], uint4 (&rv)[8]) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) rv[it] = ld_stream16(res_tile + off[it] + n);
+}
+__device__ __forceinline__ void epilogue_block64(uint32_t taddr, int n, const int (&off)[8], const float* __restrict__ bias,
+                                                 const uint4 (&rv)[8], bool has_res, bf16* __restrict__ out_tile,
+                                                 uint4* __restrict__ patch, int lane) {
+    const int c = lane & 7, rsub = lane >> 3;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -286,7 +293,7 @@ __device__ __forceinline__ void epilogue_block64(uint32_t taddr, int n, int row0
     for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + rsub;
         uint4 pk = patch[r * 8 + (c ^ (r & 7))];
-        if (res) {
+        if (has_res) {
             float f[8], fr[8];
             unpack_bf16x8(pk, f);
             unpack_bf16x8(rv[it], fr);
@@ -294,9 +301,27 @@ __device__ __forceinline__ void epilogue_block64(uint32_t taddr, int n, int row0
             for (int e = 0; e < 8; ++e) f[e] += fr[e];               // bf16 conv output + bf16 residual, one rounding
             pk = pack_bf16x8(f);
         }
-        *reinterpret_cast<uint4*>(out + idx[it]) = pk;
+        *reinterpret_cast<uint4*>(out_tile + off[it] + n) = pk;
     }
     __syncwarp();
+}
+// all 64-channel blocks of one warp's 32 rows: the residual of block i+1 is in flight while block i is processed
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(uint32_t taddr, int n0, int n_end, const int (&off)[8], const float* __restrict__ bias,
+                                              const bf16* __restrict__ res_tile, uint4 (&rv)[8], bf16* __restrict__ out_tile,
+                                              uint4* __restrict__ patch, int lane) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+        if (n0 + c0 >= n_end) break;
+        uint4 rn[8];
+        const bool more = res_tile && c0 + 64 < BN && n0 + c0 + 64 < n_end;
+        if (more) epilogue_load_residual(res_tile, n0 + c0 + 64, off, rn);
+        epilogue_block64(taddr + c0, n0 + c0, off, bias, rv, res_tile != nullptr, out_tile, patch, lane);
+        if (more) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rv[it] = rn[it];
+        }
+    }
 }
 
 struct TcGeom {
@@ -620,11 +645,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 eg.tile_pix0 = ((int64_t)b * g.H + th * g.BH) * g.W + tw * g.BW;
                 eg.W = g.W; eg.bw_shift = 31 - __clz(g.BW); eg.bw_mask = g.BW - 1; eg.Cout = g.Cout;
                 uint4* patch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 256) + (warp - 2) * 256;
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 64) {
-                    if (n0 + c0 >= g.Cout) break;
-                    epilogue_block64(taddr + c0, n0 + c0, lg * 32, eg, bias, res, out, patch, lane);
-                }
+                int off[8];
+                epilogue_row_offsets(lg * 32, eg, lane, off);
+                const bf16* res_tile = res ? res + eg.tile_pix0 * g.Cout : nullptr;
+                uint4 rv[8];
+                if (res_tile) epilogue_load_residual(res_tile, n0, off, rv);
+                epilogue_rows<BN>(taddr, n0, g.Cout, off, bias, res_tile, rv, out + eg.tile_pix0 * g.Cout, patch, lane);
             } else {
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -794,16 +820,20 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int64_t pix = ((int64_t)b * g.H + th * HALO_H + dh) * g.W + tw * HALO_W + dw;
             const int n0 = nt * BN;
             if (!stats) {
-                // residual rows are fetched (line-coalesced) before the accumulator is ready, see epilogue_block64
+                // residual rows of the first block are fetched (line-coalesced) while the main loop of this tile still runs
                 EpiGeom eg;
                 eg.tile_pix0 = ((int64_t)b * g.H + th * HALO_H) * g.W + tw * HALO_W;
                 eg.W = g.W; eg.bw_shift = 3; eg.bw_mask = HALO_W - 1; eg.Cout = g.Cout;
                 uint4* patch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512) + (warp - 2) * 256;
+                int off[8];
+                epilogue_row_offsets(lg * 32, eg, lane, off);
+                const bf16* res_tile = res ? res + eg.tile_pix0 * g.Cout : nullptr;
+                uint4 rv[8];
+                if (res_tile) epilogue_load_residual(res_tile, n0, off, rv);
                 mbar_wait(&tfull[buf], (it >> 1) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 64) epilogue_block64(taddr + c0, n0 + c0, lg * 32, eg, bias, res, out, patch, lane);
+                epilogue_rows<BN>(taddr, n0, g.Cout, off, bias, res_tile, rv, out + eg.tile_pix0 * g.Cout, patch, lane);
             } else {
                 // fused GroupNorm statistics: per-thread rows (the statistics are reduced per pixel row), residual one chunk ahead
                 const bf16* rp = res ? res + pix * g.Cout + n0 : nullptr;
