@@ -89,6 +89,15 @@ class _PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch)
 
     def forward(self, x):
+        p = self.proj.kernel_size[0]
+        if (x.is_cuda and not torch.is_grad_enabled() and torch.is_autocast_enabled() and x.shape[-1] % p == 0 and x.shape[-2] % p == 0
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+            # frozen pass: the stride = kernel conv is a plain GEMM over non-overlapping patches (cuDNN runs it as an fp32
+            # implicit-GEMM conv, 0.24 ms per step); same products, bf16 operands as autocast would give the conv
+            B, C, H, W = x.shape
+            cols = x.to(torch.bfloat16).view(B, C, H // p, p, W // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // p) * (W // p), C * p * p)
+            w = _frozen_cast(self.proj, "weight").reshape(self.proj.out_channels, -1)
+            return nn.functional.linear(cols, w, _frozen_cast(self.proj, "bias"))
         return self.proj(x).flatten(2).transpose(1, 2)
 
 
