@@ -410,7 +410,9 @@ def test_frozen_encoder_fused_glue_matches_stock_path():
             fused = enc(x)
         stock = enc(x)                                # grad mode on -> ATen ops
     assert fused.shape == stock.shape == (2, 256, 768)
-    assert rel(fused.float(), stock.float().detach()) < 2e-3
+    # bf16 tokens after 12 blocks with O(0.2) LayerScale: the two paths differ by bf16 rounding flips (the patch-embedding GEMM and
+    # the LayerNorm reassociate fp32 sums), i.e. by about one bf16 ulp (2^-8) in norm
+    assert rel(fused.float(), stock.float().detach()) < 6e-3
 
 
 def test_direct_param_grads_match_autograd_accumulation():
