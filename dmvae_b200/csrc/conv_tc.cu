@@ -1,17 +1,27 @@
 // tcgen05 implicit-GEMM convolution for sm_100a: the conv tiles of flux_ae's ResnetBlock / Upsample / AttnBlock
-// (models/flux_ae.py:32-35,63-67,101,210) in forward and data-gradient form.
+// (models/flux_ae.py:32-35,63-67,101,210,237) and of LPIPS' frozen VGG16 (utils/lpips.py:116-153) in forward,
+// data-gradient and weight-gradient form.
 //
 //   D[pixel, co] = sum_{tap, ci} X[pixel (+) tap, ci] * Wp[tap][co][ci]          M = B*H*W, N = Cout, K = taps*Cin
 //
-// * A operand (activations, channels-last bf16 [B][H][W][C]) is fetched by a 4-D tiled TMA box
-//   {64 ch, BW, BH, 1} shifted by the filter tap; out-of-image coordinates are zero-filled by the TMA unit, which
-//   is exactly the conv's zero padding.  No im2col buffer exists anywhere.
-// * B operand (tap-major packed weights [tap][Cout][Cin]) is a 3-D TMA box {64, BN, 1}.
-// * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
-// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32) into a TMEM accumulator;
-//   two accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
-// * Persistent: one CTA per SM walks tiles round-robin.  Warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
-//   alloc), warps 2..5 = epilogue (tcgen05.ld -> +bias -> bf16 [-> +residual] -> 64-byte global stores).
+// Kernels in this file (dispatch: dmvae_conv_tc_fwd / dmvae_conv_tc_wgrad at the bottom):
+//   conv_tc2h_kernel<BN>      3x3, Cout % 256 == 0: halo-resident CTA pair -- ONE (16+2)x(8+2)-pixel TMA halo per 64-channel
+//                             chunk serves all nine taps (descriptor row offsets), cta_group::2, UMMA 256 x 256 x 16
+//   conv_tcT_kernel           3x3, Cout = 64 / 128 / < 32: transposed tile, M = 128 channels, N = 256 pixels out of one halo
+//   conv_tc2_kernel<BN>       per-tap operand fetch, CTA pair (1x1, stride 2, small images)
+//   conv_tc_kernel<BN,MT>     per-tap operand fetch, single CTA, MT x 128 pixels x BN in {32,128,256}
+//   conv_tc_wgrad2_kernel<MT> weight gradient, CTA pair sharing the x tile (Cin, Cout multiples of 256)
+//   conv_tc_wgrad_kernel<..>  weight gradient, single CTA (remaining shapes)
+// Common structure:
+// * activations (channels-last bf16 [B][H][W][C]) are fetched by 4-D tiled TMA boxes; out-of-image coordinates are
+//   zero-filled by the TMA unit, which is exactly the conv's zero padding.  No im2col buffer exists anywhere.
+// * weights are tap-major packed [tap][Cout][Cin], fetched by 3-D TMA boxes {64, rows, 1}.
+// * both land in shared memory in the 128-byte-swizzled layout tcgen05.mma consumes directly (K-major for forward /
+//   dgrad, MN-major for wgrad).
+// * one elected thread issues tcgen05.mma (bf16 x bf16 -> fp32) into TMEM accumulators; two accumulator buffers let the
+//   epilogue of tile i overlap the main loop of tile i+1.
+// * persistent CTAs (one per SM, or one pair per TPC) walk tiles round-robin.  Warp 0 = TMA producer, warp 1 = MMA issuer
+//   (+TMEM alloc), the remaining warps = epilogue (tcgen05.ld -> +bias -> bf16 [-> +residual] -> global stores).
 //
 // dgrad of a stride-1 "same" conv is the same kernel fed dY and the flipped/transposed weight pack.
 #include "common.cuh"
@@ -689,7 +699,6 @@ constexpr int HALO_W = 8;       // pixels per tile row = rows per swizzle group
 constexpr int HALO_H = 16;
 
 template <int BN> struct CfgH {
-    static constexpr int A_SLOT = 40 * 1024;                    // largest halo: 5x5 filter -> 20 x 12 px x 128 B = 30 KB (3x3: 22.5 KB)
     static constexpr int A_SLOT3 = 23 * 1024;                   // 3x3: 18 x 10 px x 128 B = 23040 B, rounded to 1024
     static constexpr int B_BYTES = (BN / 2) * BK * 2;           // this CTA's half of one tap's weight tile
     static constexpr int SA = BN == 256 ? 3 : 4;

@@ -38,6 +38,7 @@ class GradArena:
         self._handles: List = []
         self._launched = [False] * len(self.bounds)
         self._slots: Dict[int, torch.Tensor] = {}
+        self._ready = set()
         self.overlap = False
         self._attach()
         self.overlap = overlap and self._distributed()
@@ -78,6 +79,7 @@ class GradArena:
         self._pending = list(self.members)
         self._launched = [False] * len(self.bounds)
         self._handles = []
+        self._ready = set()
 
     def _launch(self, c: int):
         s, e = self.bounds[c]
@@ -85,6 +87,11 @@ class GradArena:
         self._handles.append(tdist.all_reduce(self.flat[s:e], op=tdist.ReduceOp.SUM, async_op=True))
 
     def _on_grad_ready(self, p: nn.Parameter):
+        # once per parameter and step: a Function that accumulated directly reports through notify(), and autograd still
+        # runs the parameter's (empty) AccumulateGrad node with its post hooks afterwards
+        if id(p) in self._ready:
+            return
+        self._ready.add(id(p))
         c = self.chunk_of[id(p)]
         self._pending[c] -= 1
         if self._pending[c] == 0 and not self._launched[c]:

@@ -113,8 +113,9 @@ int dmvae_pack_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int
 /* 1 if the shape runs on the tcgen05 tile (stride 1, 3x3 pad 1 or 1x1, C%8==0, pixel tile divides H,W). */
 int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW);
 
-/* tcgen05 implicit GEMM.  Replaces cuDNN conv forward for nn.Conv2d at models/flux_ae.py:32-35,63,65,67,101,210
- * and -- fed dY and w_dgrad -- cuDNN's backward-data.   y = conv(x) + bias ; if residual: y = bf16(y) + residual.
+/* tcgen05 implicit GEMM.  Replaces cuDNN conv forward for nn.Conv2d at models/flux_ae.py:32-35,63,65,67,101,210,237
+ * (and utils/lpips.py:116-153, the frozen VGG16) and -- fed dY and w_dgrad -- cuDNN's backward-data.
+ * y = conv(x) + bias ; if residual: y = bf16(y) + residual.
  * gn_stats (optional, fp64 [B][32][2], caller-zeroed): the epilogue also accumulates {sum y, sum y^2} per (image,
  * GroupNorm group) of the stored bf16 values, i.e. the output of dmvae_gn_stats for the next GroupNorm(32). */
 int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
@@ -134,7 +135,13 @@ int dmvae_conv_tc_wgrad_strided(const void* x, const void* dy, float* dw_tap_maj
 /* dyz[b][2oh+1][2ow+1][c] = dy[b][oh][ow][c], zero elsewhere (bf16, C % 8 == 0). */
 int dmvae_zero_insert2x(const void* dy, void* dyz, int64_t B, int OH, int OW, int C, void* stream);
 
-/* Tuning / test hook (host only): 0 = heuristic, 1 = 128-pixel tiles per CTA, 2 = 256-pixel tiles where possible. */
+/* Tuning / test hook (host only, process-wide).  The conv entry points pick a tile per shape:
+ *   3x3, Cout % 256 == 0 ........ halo-resident CTA pair (one TMA halo serves all nine taps, cta_group::2, N = 256)
+ *   3x3, Cout = 64 / 128 / <32 .. transposed tile (M = channels, N = 256 pixels out of one halo)
+ *   1x1, stride 2, small images . per-tap operand fetch: CTA pair, or a single-CTA tile of 128 / 256 pixels
+ * mode 0 = that heuristic; 1 / 2 = force single-CTA tiles of 128 / 256 pixels; 3 = force the per-tap CTA pair;
+ * 4 / 5 = CTA pairs preferred / never; 6 / 7 = halo + transposed tiles off / on; 8 = halo + transposed tiles wherever the shape
+ * allows, ignoring the occupancy thresholds (tests); 12 / 13 / 14 = taps per CTA (2 / 3 / 4) of the 128-channel weight gradient. */
 int dmvae_conv_tc_set_tile_mode(int mode);
 
 /* tcgen05 weight gradient (both operands MN-major): dw_tap_major[tap][Cout][Cin] (fp32, caller-zeroed or

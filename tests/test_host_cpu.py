@@ -107,6 +107,48 @@ arena.zero()
 net(x_all[rank * 4:(rank + 1) * 4]).square().mean().backward()
 arena.allreduce()
 assert torch.allclose(arena.flat, ref, rtol=1e-5, atol=1e-7)
+# third step: a Function that accumulates its parameter gradients straight into the arena (what the CUDA conv / GroupNorm
+# Functions do inside GradArena.direct()) -- the chunk bookkeeping must see those parameters exactly once, via notify()
+from dmvae_b200 import ops
+
+
+class DirectLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.params = (w, b)
+        ctx.save_for_backward(x, w)
+        return x @ w.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dw, db = dy.t() @ x, dy.sum(0)
+        sw, sb = ops._grad_slot(ctx.params[0]), ops._grad_slot(ctx.params[1])
+        if sw is not None and sb is not None:
+            sw.add_(dw); sb.add_(db)
+            ops._grad_done(ctx.params[0]); ops._grad_done(ctx.params[1])
+            dw = db = None
+        return dy @ w, dw, db
+
+
+def fwd(xs):
+    h = torch.tanh(DirectLinear.apply(xs, net[0].weight, net[0].bias))
+    return DirectLinear.apply(h, net[2].weight, net[2].bias)
+
+
+assert ops._grad_slot(net[0].weight) is None, "direct mode must be off outside the context"
+arena.zero()
+with arena.direct():
+    assert ops._grad_slot(net[0].weight).data_ptr() == net[0].weight.grad.data_ptr()
+    fwd(x_all[rank * 4:(rank + 1) * 4]).square().mean().backward()
+assert all(c == 0 for c in arena._pending) and all(arena._launched), (arena._pending, arena._launched)
+arena.allreduce()
+assert torch.allclose(arena.flat, ref, rtol=1e-5, atol=1e-7), (arena.flat - ref).abs().max()
+# outside the context the same Function hands its gradients to autograd (AccumulateGrad + hooks), same result
+arena.zero()
+fwd(x_all[rank * 4:(rank + 1) * 4]).square().mean().backward()
+arena.allreduce()
+assert torch.allclose(arena.flat, ref, rtol=1e-5, atol=1e-7)
 dist.destroy_process_group()
 print("OK", rank)
 '''
