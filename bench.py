@@ -235,6 +235,7 @@ def run_ours(args):
     else:
         tr = build_trainer(dev)
     g = torch.Generator().manual_seed(42 * world + rank)
+    graphed = False
     n_pool = 4
     host = [(torch.rand(B, 3, res, res, generator=g) * 2 - 1).pin_memory() for _ in range(n_pool)]
     resident = [h.to(dev) for h in host]
@@ -263,13 +264,20 @@ def run_ours(args):
 
     for i in range(args.warmup if args.workload != "dmd" else 2 * tr.every):
         tr.step(resident[i % n_pool])
+    if args.cuda_graph and args.workload == "tokenizer":
+        graphed = tr.capture_cuda_graph(resident[0])
+        _lib.Stats.reset()
+        tr._forward_backward(resident[0])                       # count the launches a replay stands for
+        graph_launches = _lib.Stats.launches + 2                # + the two optimizer kernels issued eagerly
+        for i in range(2):
+            tr.step(resident[i % n_pool])
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     _lib.Stats.reset()
     ms = timed(lambda i: tr.step(resident[i % n_pool]), args.steps)
     host_issue_ms = host_issue["ms"]
-    launches = _lib.Stats.launches
+    launches = _lib.Stats.launches if not graphed else graph_launches * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end: pinned host batch in, loss out, every step
@@ -287,10 +295,15 @@ def run_ours(args):
     _lib.Stats.work_fn = _work
     _lib.Stats.timing = True
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    saved_graph = getattr(tr, "_graph", None)
+    if graphed:
+        tr._graph = None                         # the profiled step runs eagerly so that every launch can be bracketed by events
     pe0.record()
     tr.step(resident[0])                         # (dmd workload: the iteration counter is back at a VAE turn here)
     pe1.record()
     torch.cuda.synchronize()
+    if graphed:
+        tr._graph = saved_graph
     _lib.Stats.timing = False
     prof_total_ms = pe0.elapsed_time(pe1)
     per = {}
@@ -338,7 +351,7 @@ def run_ours(args):
                    "flow-matching step; allreduce, clip, AdamW per network; steps rounded up to whole 5-iteration cycles"}[args.workload],
                    "per_gpu_batch": B, "global_batch": B * world,
                    "image": f"3x{res}x{res}", "z_channels": 16 if args.workload == "stress512" else 32, "parallelism": f"dp{world}",
-                   "weights": "random init (seed 42)",
+                   "weights": "random init (seed 42)", "cuda_graph": graphed,
                    "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; 4 rotating input batches"},
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": B * 3 * res * res * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last.get("loss")},
@@ -460,6 +473,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
+                    help="tokenizer workload: issue every kernel from Python instead of replaying forward+backward from a CUDA graph")
     ap.add_argument("--workload", default="tokenizer", choices=["tokenizer", "stress512", "dmd"],
                     help="tokenizer = BASELINE configs[1] (the headline workload); dmd = configs[2]; stress512 = configs[4] "
                          "(no CPU baseline for the last two)")

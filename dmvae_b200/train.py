@@ -142,17 +142,62 @@ class TokenizerTrainer:
         self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=wd, betas=(0.9, 0.95), eps=1e-8, fused=self.params[0].is_cuda)
         self.ema = [p.detach().clone() for p in self.params] if ema else None
 
-    def step(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def _forward_backward(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
         self.arena.zero()
         with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
             recon = self.vae(images, freeze_encoder=True)
             loss, log = self.loss_fn.forward_generator(images, recon)
         with self.arena.direct():                   # conv / GroupNorm gradients accumulate straight into the arena
             loss.backward()
+        log["loss"] = loss.detach()
+        return log
+
+    def capture_cuda_graph(self, example_images: torch.Tensor, warmup: int = 2) -> bool:
+        """Capture forward + backward of one step (≈1100 kernel launches at fixed shapes) into a CUDA graph; ``step`` then copies
+        the batch into the graph's input buffer and replays it, leaving only the gradient exchange and the two optimizer
+        kernels (whose step count / learning rate are host-side scalars) to be issued from Python.  With several ranks the NCCL
+        exchange is issued after the replay (0.5 ms for 207 MB over NVLink, not overlapped).  Returns False -- and stays eager --
+        if capture fails."""
+        if self.fused is None or not example_images.is_cuda:
+            return False
+        self._graph = None
+        self.arena.hooks_enabled = False            # nothing may enqueue a collective from inside the captured backward
+        try:
+            self._gx = example_images.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):           # warm up off the default stream: kernel attributes, tensor maps, cuDNN / cuBLAS plans
+                for _ in range(max(1, warmup)):
+                    self._forward_backward(self._gx)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            # the bf16 operand packs are refreshed only when a parameter's version counter moved: make sure the refresh is part
+            # of what gets captured, so that every replay re-packs the weights the optimizer has just updated
+            torch.autograd.graph.increment_version(self.params)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._glog = self._forward_backward(self._gx)
+            self._graph = graph
+            return True
+        except Exception as e:                      # noqa: BLE001 -- any capture problem means: keep the eager path
+            import warnings
+            warnings.warn(f"TokenizerTrainer: CUDA graph capture failed ({type(e).__name__}: {e}); staying eager")
+            self._graph = None
+            self.arena.hooks_enabled = True
+            torch.cuda.synchronize()
+            return False
+
+    def step(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+        if getattr(self, "_graph", None) is not None and images.shape == self._gx.shape:
+            self._gx.copy_(images, non_blocking=True)
+            self._graph.replay()
+            log = dict(self._glog)
+        else:
+            log = self._forward_backward(images)
+        loss = log["loss"]
         self.arena.allreduce()
         if self.fused is not None:                  # clip + AdamW + EMA in two kernels over the flat arenas
             log["vae_norm"] = self.fused.step()
-            log["loss"] = loss.detach()
             return log
         # clip_grad_norm_(params, 1.0) (train_tokenizer.py:415) on the flat arena: one norm, one scale
         total = torch.linalg.vector_norm(self.arena.flat, 2)

@@ -39,6 +39,7 @@ class GradArena:
         self._launched = [False] * len(self.bounds)
         self._slots: Dict[int, torch.Tensor] = {}
         self._ready = set()
+        self.hooks_enabled = True          # False: no exchange is issued from backward (CUDA-graph replay); allreduce() does it all
         self.overlap = False
         self._attach()
         self.overlap = overlap and self._distributed()
@@ -89,7 +90,7 @@ class GradArena:
     def _on_grad_ready(self, p: nn.Parameter):
         # once per parameter and step: a Function that accumulated directly reports through notify(), and autograd still
         # runs the parameter's (empty) AccumulateGrad node with its post hooks afterwards
-        if id(p) in self._ready:
+        if not self.hooks_enabled or id(p) in self._ready:
             return
         self._ready.add(id(p))
         c = self.chunk_of[id(p)]

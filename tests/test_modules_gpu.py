@@ -451,3 +451,34 @@ def test_direct_param_grads_match_autograd_accumulation():
     for p in arena.params:
         assert p.grad.data_ptr() == arena.flat.data_ptr() + 4 * off
         off += p.numel()
+
+
+def test_tokenizer_trainer_cuda_graph_matches_eager():
+    """capture_cuda_graph(): forward + backward replayed from a CUDA graph must train like the eager step (same weights, same
+    batches; bf16 run-to-run noise only), and keeps working after the capture for several replays."""
+    from dmvae_b200.vae import VAE
+    from dmvae_b200.lpips import LPIPS
+    from dmvae_b200.train import LossConfig, TokenizerTrainer, VAELossFunction
+
+    def make():
+        torch.manual_seed(0)
+        vae = VAE(z_channels=32, model_size="base").to(DEV)
+        vae.encoder.eval()
+        for p in vae.encoder.parameters():
+            p.requires_grad = False
+        lp = LPIPS(ckpt_path=None, pretrained_vgg=False).eval().to(DEV)
+        return TokenizerTrainer(vae, VAELossFunction(LossConfig(), lpips_loss=lp), lr=2e-4)
+
+    g = torch.Generator(device=DEV).manual_seed(5)
+    batches = [torch.rand(2, 3, 256, 256, device=DEV, generator=g) * 2 - 1 for _ in range(4)]
+    eager, graphed = make(), make()
+    assert graphed.capture_cuda_graph(batches[0])                # warm-up passes compute gradients only: weights still equal
+    le, lg = [], []
+    for x in batches:
+        le.append(eager.step(x)["loss"].item())
+        lg.append(graphed.step(x)["loss"].item())
+    for a, b in zip(le, lg):
+        assert abs(a - b) <= 1e-2 * abs(a), (le, lg)
+    pe = torch.cat([p.detach().reshape(-1) for p in eager.params])
+    pg = torch.cat([p.detach().reshape(-1) for p in graphed.params])
+    assert rel(pg, pe) < 1e-2
