@@ -482,3 +482,26 @@ def test_tokenizer_trainer_cuda_graph_matches_eager():
     pe = torch.cat([p.detach().reshape(-1) for p in eager.params])
     pg = torch.cat([p.detach().reshape(-1) for p in graphed.params])
     assert rel(pg, pe) < 1e-2
+
+
+def test_decoder_production_size_against_reference_outputs():
+    """The production decoder on the GPU (bf16 pipeline, every layer on its production kernel, fwd + bwd) against what the REAL
+    reference module (fp32, CPU) produced for the same weights and tokens: tests/golden/decoder_full.pt (make_golden_full.py).
+    Tolerances: bf16 pipeline vs fp32 pipeline -- 3e-2 on the image and the last layer, 8e-2 on gradients ~20 roundings deep
+    (the oracle's own fp32-vs-bf16 gap there is 3-6e-2)."""
+    c = torch.load(os.path.join(G, "decoder_full.pt"), weights_only=True)["decoder_full"]
+    sd = O.make_decoder_state(z_channels=32, seed=c["seed"], randomize_affine=True)
+    dec = _decoder(sd, ch=128, out_ch=3, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, resolution=256, z_channels=16)
+    g = torch.Generator().manual_seed(c["dy_seed"])
+    z = torch.randn(1, 256, 32, generator=g)
+    assert torch.equal(z, c["z"])
+    zc = z.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = dec(zc)
+    assert rel(y.float(), c["y"].float()) < 3e-2
+    dy = torch.randn(y.shape, generator=g) / y.numel()
+    y.float().backward(dy.to(DEV))
+    assert rel(zc.grad, c["dz"]) < 8e-2
+    params = dict(dec.named_parameters())
+    for name, ref in c["dparams"].items():
+        assert rel(params[name].grad, ref) < (3e-2 if name.startswith(("conv_out", "norm_out")) else 8e-2), name

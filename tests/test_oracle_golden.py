@@ -124,3 +124,50 @@ def test_latents_to_spatial_bit_exact():
     x = torch.randn(2, 16, 5)
     y = O.latents_to_spatial(x)
     assert y.shape == (2, 5, 4, 4) and torch.equal(y[1, 3, 2, 1], x[1, 9, 3])
+
+
+# ---------------------------------------------------------------- production-size pins (tests/golden/make_golden_full.py)
+FULL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decoder_full.pt")
+
+
+def test_decoder_production_size_against_reference():
+    """The oracle's Decoder at production size (49.6 M parameters regenerated from the fixture's seed) against outputs and
+    gradients the REAL reference module produced for the same weights and tokens."""
+    c = torch.load(FULL, weights_only=True)["decoder_full"]
+    sd = {k: v.requires_grad_(True) for k, v in O.make_decoder_state(z_channels=32, seed=c["seed"], randomize_affine=True).items()}
+    g = torch.Generator().manual_seed(c["dy_seed"])
+    z = torch.randn(1, 256, 32, generator=g)
+    assert torch.equal(z, c["z"])
+    z.requires_grad_(True)
+    y = O.decoder_forward(sd, z)
+    assert y.shape == (1, 3, 256, 256)
+    assert rel(y, c["y"].float()) < 1e-3                      # stored as fp16
+    dy = torch.randn(y.shape, generator=g) / y.numel()
+    y.backward(dy)
+    assert rel(z.grad, c["dz"]) < 1e-4
+    for name, ref in c["dparams"].items():
+        assert rel(sd[name].grad, ref) < 1e-4, name
+
+
+@pytest.mark.parametrize("cin,cout", [(512, 512), (512, 256), (256, 256), (256, 128), (128, 128)])
+def test_resnet_block_decoder_channel_configs(cin, cout):
+    """ResnetBlock (flux_ae.py:55-82) at the decoder's remaining channel configurations, weights regenerated from the seed."""
+    c = torch.load(FULL, weights_only=True)[f"resnet_{cin}_{cout}"]
+    gb = torch.Generator().manual_seed(c["seed"])
+    shapes = [("norm1.weight", (cin,)), ("norm1.bias", (cin,)), ("conv1.weight", (cout, cin, 3, 3)), ("conv1.bias", (cout,)),
+              ("norm2.weight", (cout,)), ("norm2.bias", (cout,)), ("conv2.weight", (cout, cout, 3, 3)), ("conv2.bias", (cout,))]
+    if cin != cout:
+        shapes += [("nin_shortcut.weight", (cout, cin, 1, 1)), ("nin_shortcut.bias", (cout,))]
+    sd = {}
+    for n, s in shapes:                                       # the generation rule of make_golden_full.py, same order
+        if len(s) > 1:
+            sd["b." + n] = torch.randn(s, generator=gb) * 0.02
+        elif "norm" in n and n.endswith("weight"):
+            sd["b." + n] = 1 + 0.1 * torch.randn(s, generator=gb)
+        else:
+            sd["b." + n] = 0.05 * torch.randn(s, generator=gb)
+    x = torch.randn(1, cin, c["hw"], c["hw"], generator=gb, requires_grad=True)
+    y = O.resnet_block(sd, "b", x)
+    dy = torch.randn(y.shape, generator=gb)
+    (dx,) = torch.autograd.grad(y, x, dy)
+    assert rel(y, c["y"].float()) < 1e-3 and rel(dx, c["dx"].float()) < 1e-3      # fixtures stored as fp16
