@@ -505,3 +505,21 @@ def test_decoder_production_size_against_reference_outputs():
     params = dict(dec.named_parameters())
     for name, ref in c["dparams"].items():
         assert rel(params[name].grad, ref) < (3e-2 if name.startswith(("conv_out", "norm_out")) else 8e-2), name
+
+
+@pytest.mark.parametrize("tag,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+def test_dmd_zero_normaliser_against_reference_golden(tag, tol):
+    """The fused DMD kernel on a batch holding a sample with w_b = 0 and a zero numerator (0/0 -> NaN -> 0, train_dmd.py:222-224)
+    against the real reference method's output (tests/golden/dmd_edge.pt)."""
+    from dmvae_b200.train import LossConfig, VAELossFunction
+    c = torch.load(os.path.join(G, "dmd_edge.pt"), weights_only=True)[tag]
+    dev = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in c.items()}
+    fn = VAELossFunction(LossConfig(dmd_cfg_scale=1.0, num_classes=1000), sit=lambda xt, t, y: dev["Sc"], base_model=lambda xt, t, y: dev["Tc"])
+    z = dev["z"].clone().requires_grad_(True)
+    loss, log = fn.compute_distribution_matching_loss(z, torch.zeros(4, dtype=torch.long, device=DEV), t=dev["t"], x0=dev["x0"])
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(z.grad).all()
+    assert float(z.grad[0].abs().max()) == 0.0
+    assert abs(loss.item() - c["loss"].item()) <= tol * abs(c["loss"].item())
+    assert abs(log["dmd_gradient_norm"].item() - c["gnorm"]) <= tol * abs(c["gnorm"])
+    assert rel(z.grad.float(), c["dz"].float()) <= tol

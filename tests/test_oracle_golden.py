@@ -171,3 +171,17 @@ def test_resnet_block_decoder_channel_configs(cin, cout):
     dy = torch.randn(y.shape, generator=gb)
     (dx,) = torch.autograd.grad(y, x, dy)
     assert rel(y, c["y"].float()) < 1e-3 and rel(dx, c["dx"].float()) < 1e-3      # fixtures stored as fp16
+
+
+@pytest.mark.parametrize("tag,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+def test_dmd_zero_normaliser_nan_to_num(tag, tol):
+    """A sample with w_b = mean|p_real| = 0 and a zero numerator: grad = 0/0 = NaN -> 0 (train_dmd.py:222-224), pinned on the real
+    reference method (tests/golden/make_golden_dmd_edge.py).  The sample contributes nothing; the others are unaffected."""
+    c = torch.load(os.path.join(G, "dmd_edge.pt"), weights_only=True)[tag]
+    xt = O.dmd_mix_xt(c["z"], c["x0"], c["t"])
+    loss, gnorm, dz = O.dmd_loss(c["z"], xt, c["t"], c["Tc"], c["Sc"], None, None, 1.0, True)
+    assert torch.isfinite(loss) and torch.isfinite(dz).all()
+    assert float(dz[0].abs().max()) == 0.0 and float(c["dz"][0].abs().max()) == 0.0
+    assert abs(loss.item() - c["loss"].item()) <= tol * abs(c["loss"].item())
+    assert abs(gnorm.item() - c["gnorm"]) <= tol * abs(c["gnorm"])
+    assert rel(dz, c["dz"].float()) <= tol
