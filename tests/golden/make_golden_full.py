@@ -52,6 +52,18 @@ def main():
         dyb = torch.randn(yb.shape, generator=gb)
         (dx,) = torch.autograd.grad(yb, x, dyb)
         out[f"resnet_{cin}_{cout}"] = dict(seed=cin + cout, hw=hw, y=yb.detach().half(), dx=dx.half())
+    # A2 Encoder at production size (config 5's module, models/flux_ae.py:110-181), weights regenerated from the seed
+    enc = R.Encoder(resolution=256, in_channels=3, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=16)
+    esd = O.make_encoder_state(z_channels=16, seed=SEED + 2, randomize_affine=True)
+    enc.load_state_dict(esd, strict=True)
+    ge = torch.Generator().manual_seed(SEED + 3)
+    x = (torch.rand(1, 3, 256, 256, generator=ge) * 2 - 1).requires_grad_(True)
+    h = enc(x)
+    dh = torch.randn(h.shape, generator=ge)
+    eparams = dict(enc.named_parameters())
+    enames = ["conv_in.weight", "down.0.block.0.conv1.weight", "down.1.downsample.conv.bias", "mid.attn_1.norm.weight", "conv_out.weight"]
+    eg = torch.autograd.grad(h, [x] + [eparams[n] for n in enames], dh)
+    out["encoder_full"] = dict(seed=SEED + 2, x_seed=SEED + 3, y=h.detach(), dx=eg[0].half(), dparams={n: gr for n, gr in zip(enames, eg[1:])})
     torch.save(out, os.path.join(HERE, "decoder_full.pt"))
     print({k: (list(v.keys())) for k, v in out.items()})
 

@@ -185,3 +185,20 @@ def test_dmd_zero_normaliser_nan_to_num(tag, tol):
     assert abs(loss.item() - c["loss"].item()) <= tol * abs(c["loss"].item())
     assert abs(gnorm.item() - c["gnorm"]) <= tol * abs(c["gnorm"])
     assert rel(dz, c["dz"].float()) <= tol
+
+
+def test_encoder_production_size_against_reference():
+    """The oracle's Encoder at production size (models/flux_ae.py:110-181; BASELINE configs[4]'s module) against the real reference
+    module's output and gradients for weights regenerated from the fixture's seed."""
+    c = torch.load(FULL, weights_only=True)["encoder_full"]
+    sd = {k: v.requires_grad_(True) for k, v in O.make_encoder_state(z_channels=16, seed=c["seed"], randomize_affine=True).items()}
+    g = torch.Generator().manual_seed(c["x_seed"])
+    x = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).requires_grad_(True)
+    h = O.encoder_forward(sd, x)
+    assert h.shape == c["y"].shape == (1, 32, 32, 32)
+    assert rel(h, c["y"]) < 1e-4
+    dh = torch.randn(h.shape, generator=g)
+    h.backward(dh)
+    assert rel(x.grad, c["dx"].float()) < 2e-3                # stored as fp16
+    for name, ref in c["dparams"].items():
+        assert rel(sd[name].grad, ref) < 1e-4, name
