@@ -183,3 +183,22 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+@pytest.mark.parametrize("case", ["decoder_std", "decoder_xavier", "encoder_std"])
+def test_initial_weights_reproduce_reference_bit_for_bit(case):
+    """Same seed => the same initial weights as the reference's modules + models/init_param.py (tests/golden/init.pt holds per-tensor
+    checksums produced by the real reference): module registration order, RNG consumption and the init rules all match."""
+    from dmvae_b200 import autoencoder
+    from dmvae_b200.vae import init_weights
+    c = torch.load(os.path.join(G, "init.pt"), weights_only=True)[case]
+    mod = getattr(autoencoder, c["kind"])(**c["kw"])
+    if c["post"] is not None:
+        mod.post_init(c["post"])
+    torch.manual_seed(c["seed"])
+    init_weights(mod, c["arg"])
+    sd = mod.state_dict()
+    assert list(sd.keys()) == list(c["sums"].keys())
+    for k, (s, a, head) in c["sums"].items():
+        v = sd[k]
+        assert float(v.double().sum()) == s and float(v.double().abs().sum()) == a and torch.equal(v.reshape(-1)[:4], head), k
