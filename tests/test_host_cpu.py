@@ -202,3 +202,18 @@ def test_initial_weights_reproduce_reference_bit_for_bit(case):
     for k, (s, a, head) in c["sums"].items():
         v = sd[k]
         assert float(v.double().sum()) == s and float(v.double().abs().sum()) == a and torch.equal(v.reshape(-1)[:4], head), k
+
+
+@pytest.mark.parametrize("tag", ["fp32_shift1.0", "bf16_shift1.0", "fp32_shift3.0", "bf16_shift3.0"])
+def test_sample_t_x0_reproduces_reference_transport_sample(tag):
+    """train.sample_t_x0 vs the real Transport.sample (transport.py:105-116, tests/golden/transport.pt): same draws in the same order
+    (x0 from the default generator, then t on the CPU generator, cast to the latents' dtype, then the time shift)."""
+    from dmvae_b200.train import sample_t_x0
+    c = torch.load(os.path.join(G, "transport.pt"), weights_only=True)[tag]
+    dtype = torch.float32 if c["dtype"] == "fp32" else torch.bfloat16
+    torch.manual_seed(123)
+    x1 = torch.randn(6, 32, 16, 16).to(dtype)
+    torch.manual_seed(77)
+    t, x0 = sample_t_x0(x1, c["shift"])
+    assert t.dtype == dtype and torch.equal(t, c["t"])
+    assert float(x0.double().sum()) == c["x0_sum"] and torch.equal(x0.reshape(-1)[:8], c["x0_head"])
