@@ -233,3 +233,30 @@ def test_update_ema_matches_reference_arithmetic():
         update_ema(ema_ours, params, 0.9999)
         params = [p + 0.01 for p in params]
     assert all(torch.equal(a, b) for a, b in zip(ema_ref, ema_ours))
+
+
+def test_abi_rejects_null_pointers_without_touching_the_device():
+    """Error convention of the C ABI: every compute entry point validates its arguments before any CUDA call, returns a
+    negative status and leaves a message naming itself in dmvae_last_error() -- checkable on a box without a GPU."""
+    import ctypes
+    from dmvae_b200 import _lib
+    lib = _lib.load()
+    lib.dmvae_last_error.restype = ctypes.c_char_p
+    checked = 0
+    for name, sig in _lib.SIGNATURES.items():
+        if ctypes.c_void_p not in sig or name in ("dmvae_check_device",):
+            continue
+        args = []
+        for ty in sig[:-1]:                                   # the last slot is the stream
+            if ty is ctypes.c_void_p:
+                args.append(None)
+            elif ty is ctypes.c_float or ty is ctypes.c_double:
+                args.append(ty(0.5))
+            else:
+                args.append(ty(1))
+        rc = getattr(lib, name)(*args, None)
+        msg = lib.dmvae_last_error().decode()
+        assert rc < 0, f"{name} accepted null pointers (rc={rc})"
+        assert name.replace("dmvae_", "").split("_fwd")[0].split("_bwd")[0][:6] in msg or "null" in msg or "pointer" in msg, (name, msg)
+        checked += 1
+    assert checked >= 25
