@@ -46,7 +46,7 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region: NVML in a thread (10 ms period), nvidia-smi fallback."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in a thread (20 ms period), nvidia-smi fallback."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
@@ -69,7 +69,7 @@ class ClockSampler:
                         self.mask |= int(reasons_fn(h))
                     except Exception:
                         pass
-                    time.sleep(0.01)
+                    time.sleep(0.02)
             self.th = threading.Thread(target=loop, daemon=True)
             self.th.start()
         except Exception:
