@@ -24,15 +24,12 @@ def pytest_collection_modifyitems(config, items):
 
 
 def pytest_sessionstart(session):
-    """Build libdmvae_b200.so when it is missing or older than its sources (fresh clone, edited kernel): the tests bind the
-    in-tree library, there is nothing else to fall back to.  Needs nvcc; if the build fails the tests that load the library fail
-    with its own message."""
-    import glob
+    """Build libdmvae_b200.so when it is missing (fresh clone: built artefacts are not in the history): the tests bind the in-tree
+    library, there is nothing else to fall back to.  Needs nvcc; if the build fails, the tests that load the library fail with
+    its own message."""
     import shutil
     lib = os.path.join(ROOT, "dmvae_b200", "libdmvae_b200.so")
-    srcs = glob.glob(os.path.join(ROOT, "dmvae_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
-    stale = (not os.path.exists(lib)) or any(os.path.getmtime(f) > os.path.getmtime(lib) for f in srcs)
-    if stale and shutil.which("nvcc"):
+    if not os.path.exists(lib) and shutil.which("nvcc"):
         try:
             from dmvae_b200 import build
             build.build()
