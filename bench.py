@@ -13,7 +13,11 @@ reconstruction loss, backward through the decoder, gradient allreduce, clip, Ada
 One JSON line on stdout (rank 0).  `value` = device-resident inputs, no host syncs in the timed region;
 `e2e` = the same K steps through the public API with pinned HOST image batches copied in and the loss read back
 every step.  `roofline` is the tcgen05 conv tile (forward + data-gradient launches) timed with CUDA events around
-every launch of one extra profiled step; `cpu_baseline` is the oracle step timed on a bounded sample (1 image).
+every launch of one extra profiled step; `roofline_hbm` is the fused DMD loss kernel at a bandwidth-bound size (64 Mi
+latents); `dmd_stage` is the train_dmd.py iteration (BASELINE configs[2]) replayed from CUDA graphs; `gpu_baseline` is the
+same tokenizer step through stock PyTorch/cuDNN eager on the same GPU (the reference's real execution path);
+`loss_parity` is the 100-step loss comparison of the real trainer against a strict-fp32 anchor and a cuDNN-autocast
+control arm (scripts/loss_parity.py); `cpu_baseline` is the oracle step timed on a bounded sample (1 image).
 """
 from __future__ import annotations
 
@@ -201,6 +205,10 @@ class DmdStageTrainer:
         self.every, self.it = vae_train_every, 0
         self.labels = None
 
+    def capture(self, images):
+        self.labels = torch.randint(0, 1000, (images.shape[0],), device=images.device)
+        return self.tr.capture_cuda_graphs(images, self.labels, strict=True)
+
     def step(self, images):
         if self.labels is None or self.labels.shape[0] != images.shape[0]:
             self.labels = torch.randint(0, 1000, (images.shape[0],), device=images.device)
@@ -209,6 +217,147 @@ class DmdStageTrainer:
         log = self.tr.step(images, self.labels, vae_turn=turn)
         log.setdefault("loss", log["diffusion_loss"])
         return log
+
+
+WORKLOADS = {
+    "tokenizer": "train_tokenizer.py VAE pretrain step (BASELINE configs[1]): frozen ViT-L/16 encoder, flux Decoder "
+                 "fwd+bwd, L1+LPIPS(VGG16), allreduce, clip, AdamW, EMA",
+    "stress512": "BASELINE configs[4] stress: flux_ae Encoder -> reparam+KL -> Decoder fwd+bwd at 512x512, L1 + KL, "
+                 "allreduce, clip, AdamW, EMA",
+    "dmd": "train_dmd.py iteration (BASELINE configs[2]): LightningDiT-Mini/1 teacher+student; every 5th iteration is a VAE "
+           "turn (trainable ViT-L/16 encoder + flux Decoder fwd+bwd, L1+LPIPS+10*DMD cfg 5), every iteration a student "
+           "flow-matching step; allreduce, clip, AdamW per network; steps rounded up to whole 5-iteration cycles",
+}
+
+
+def workload_config(workload, B, world, res):
+    """`config` of the JSON line: names the workload; identical for our arm and the reference arm."""
+    return {"workload": WORKLOADS[workload], "per_gpu_batch": B, "global_batch": B * world, "image": f"3x{res}x{res}",
+            "z_channels": 16 if workload == "stress512" else 32, "parallelism": f"dp{world}", "weights": "random init (seed 42)"}
+
+
+def _timed(fn, steps, world, dev):
+    """K calls of fn bracketed by barrier + synchronize; device time by CUDA events, MAX over ranks.  Returns (ms, host issue ms/step)."""
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        fn(i)
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps          # host time to ISSUE a step (no device wait)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item(), host_ms
+
+
+def measure_dmd_stage(dev, world, rank, B, cycles=2):
+    """BASELINE configs[2] as a secondary measured workload: the train_dmd.py iteration (VAE turn every 5th iteration + student
+    step every iteration) replayed from three CUDA graphs, NCCL exchange inside the graphs.  Whole 5-iteration cycles are timed."""
+    from dmvae_b200 import _lib
+    tr = DmdStageTrainer(dev)
+    g = torch.Generator().manual_seed(4242 * world + rank)
+    xs = [(torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).to(dev) for _ in range(2)]
+    for i in range(tr.every):                                    # eager warm-up: one full cycle
+        tr.step(xs[i % 2])
+    tr.it = 0
+    _lib.Stats.reset()
+    for i in range(tr.every):                                    # launches of one cycle (library kernels only), counted eagerly
+        tr.step(xs[i % 2])
+    lib_launches_per_cycle = _lib.Stats.launches
+    tr.it = 0
+    tr.capture(xs[0])
+    for i in range(tr.every):
+        tr.step(xs[i % 2])
+    steps = cycles * tr.every
+    ms, host_ms = _timed(lambda i: tr.step(xs[i % 2]), steps, world, dev)
+    out = {"workload": WORKLOADS["dmd"], "value": round(world * B * steps / (ms * 1e-3), 2), "unit": UNIT,
+           "ms_per_iteration": round(ms / steps, 3), "iterations": steps, "host_issue_ms_per_iteration": round(host_ms, 3),
+           "cuda_graph": tr.tr.graphed, "exchange": tr.tr.exchange_mode, "per_gpu_batch": B,
+           "library_launches_per_5_iterations": lib_launches_per_cycle,
+           "exchange_bytes_per_vae_turn": 4 * tr.tr.arena_vae.flat.numel(), "exchange_bytes_per_student_step": 4 * tr.tr.arena_sit.flat.numel()}
+    del tr
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_dmd_kernel_roofline(dev, peaks, latents=64 << 20, reps=10):
+    """The fused DMD loss + gradient kernel (train_dmd.py:214-228) at a bandwidth-bound size (at the real B=16 size it
+    moves 1.8 MB and is launch-bound).  Algorithmic bytes: 6 bf16 reads + 1 bf16 write = 14 B per latent element.  Timed with
+    CUDA events on the launching stream; 940 MB of operands per launch exceeds the 126 MB L2, so every launch streams from HBM."""
+    from dmvae_b200 import losses
+    P = 32 * 16 * 16
+    Bn = latents // P
+    g = torch.Generator(device=dev).manual_seed(7)
+    z, xt, vTc, vTu, vSc, vSu = (torch.randn(Bn, 32, 16, 16, device=dev, generator=g).bfloat16() for _ in range(6))
+    t = torch.rand(Bn, device=dev, generator=g).bfloat16()
+
+    def once():
+        return losses.dmd_loss(z, xt, t, vTc, vSc, vTu, vSu, 5.0, True, dz_dtype=torch.bfloat16)
+    from dmvae_b200 import _lib
+    for _ in range(3):
+        once()
+    _lib.Stats.reset()
+    _lib.Stats.timing = True
+    _lib.Stats.work_fn = lambda name, a: 14.0 * Bn * P if name == "dmvae_dmd_loss_fwd_bwd" else 0.0
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    _lib.Stats.timing = False
+    ts = [a.elapsed_time(b) for n, a, b, w in _lib.Stats.events if n == "dmvae_dmd_loss_fwd_bwd"]
+    ms = sum(ts) / len(ts)
+    byts = 14.0 * Bn * P
+    ach = byts / (ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r02_dmd_kernel_ncu.json")     # dram bytes of one launch at this size from an ncu --set full capture
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    return {"bound": "hbm", "kernel": "dmd_loss_bf16x2_kernel (fused DMD loss + dz, losses.cu)", "achieved": round(ach, 1),
+            "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "peak_source": peaks["src"],
+            "traffic": traffic, "algorithmic_bytes_per_launch": byts, "latent_elements": Bn * P, "avg_launch_ms": round(ms, 4),
+            "launches_timed": len(ts), "real_size_note": "B=16 moves 1.8 MB: launch-latency bound (SURVEY D7)"}
+
+
+def measure_gpu_baseline(dev, B, steps=5, warmup=3):
+    """The real bar: the same tokenizer step through stock PyTorch / cuDNN eager under torch.autocast(bf16) with cudnn.benchmark on
+    (the reference's own execution path on a GPU), same box, same weights shape, same batch.  scripts/stock_arms.py."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import stock_arms
+    from oracle import dmvae_oracle as O
+    from dmvae_b200.vae import DINOEncoder, MLP
+    torch.manual_seed(42)
+    enc = DINOEncoder("large").eval().to(dev)
+    mlp = MLP(1024, 32).to(dev)
+    sd = {k: v.to(dev) for k, v in O.make_decoder_state(z_channels=32, seed=42).items()}
+    lp = {k: v.to(dev) for k, v in O.make_lpips_state(seed=42).items()}
+    arm = stock_arms.StockStep(enc, mlp, sd, lp, "autocast", lr=1e-4)
+    x = torch.rand(B, 3, 256, 256, device=dev) * 2 - 1
+    for _ in range(warmup):
+        arm.step(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        arm.step(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del arm
+    torch.cuda.empty_cache()
+    return {"value": round(B / ms * 1e3, 2), "unit": UNIT, "ms_per_step": round(ms, 2), "steps": steps, "warmup": warmup,
+            "kind": "stock PyTorch + cuDNN eager, torch.autocast(bf16), cudnn.benchmark=True, torch.optim.AdamW (no EMA pass); "
+                    "device-resident input; oracle's functional restatement of the reference modules"}
 
 
 def run_ours(args):
@@ -236,48 +385,36 @@ def run_ours(args):
         tr = build_trainer(dev)
     g = torch.Generator().manual_seed(42 * world + rank)
     graphed = False
+    exchange_mode = "eager"
     n_pool = 4
     host = [(torch.rand(B, 3, res, res, generator=g) * 2 - 1).pin_memory() for _ in range(n_pool)]
     resident = [h.to(dev) for h in host]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    host_issue = {}
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            fn(i)
-        host_issue["ms"] = (time.perf_counter() - t0) * 1e3 / steps      # host time to ISSUE a step (no device wait)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
     for i in range(args.warmup if args.workload != "dmd" else 2 * tr.every):
         tr.step(resident[i % n_pool])
+    graph_launches = None
     if args.cuda_graph and args.workload == "tokenizer":
-        graphed = tr.capture_cuda_graph(resident[0])
+        # launches a replay stands for: an eager pass with the weight re-packs included (version counters bumped)
+        torch.autograd.graph.increment_version(tr.params)
         _lib.Stats.reset()
-        tr._forward_backward(resident[0])                       # count the launches a replay stands for
+        tr._forward_backward(resident[0])
         graph_launches = _lib.Stats.launches + 2                # + the two optimizer kernels issued eagerly
+        tr.capture_cuda_graph(resident[0], strict=True)         # bench mode: a capture failure is an error, not a silent eager run
+        graphed, exchange_mode = tr.graphed, tr.exchange_mode
         for i in range(2):
+            tr.step(resident[i % n_pool])
+    elif args.cuda_graph and args.workload == "dmd":
+        tr.it = 0
+        tr.capture(resident[0])
+        graphed, exchange_mode = tr.tr.graphed, tr.tr.exchange_mode
+        for i in range(tr.every):
             tr.step(resident[i % n_pool])
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     _lib.Stats.reset()
-    ms = timed(lambda i: tr.step(resident[i % n_pool]), args.steps)
-    host_issue_ms = host_issue["ms"]
-    launches = _lib.Stats.launches if not graphed else graph_launches * args.steps
+    ms, host_issue_ms = _timed(lambda i: tr.step(resident[i % n_pool]), args.steps, world, dev)
+    launches = _lib.Stats.launches if graph_launches is None else graph_launches * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end: pinned host batch in, loss out, every step
@@ -288,40 +425,55 @@ def run_ours(args):
         last["loss"] = tr.step(x)["loss"].item()
     for i in range(1 if args.workload != "dmd" else tr.every):
         e2e_step(i)
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e, _ = _timed(e2e_step, args.steps, world, dev)
 
-    # one profiled step: CUDA events around every library launch
-    _lib.Stats.reset()
-    _lib.Stats.work_fn = _work
-    _lib.Stats.timing = True
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    saved_graph = getattr(tr, "_graph", None)
-    if graphed:
-        tr._graph = None                         # the profiled step runs eagerly so that every launch can be bracketed by events
-    pe0.record()
-    tr.step(resident[0])                         # (dmd workload: the iteration counter is back at a VAE turn here)
-    pe1.record()
-    torch.cuda.synchronize()
-    if graphed:
-        tr._graph = saved_graph
-    _lib.Stats.timing = False
-    prof_total_ms = pe0.elapsed_time(pe1)
-    per = {}
-    dump = []
-    for name, a, b, work in _lib.Stats.events:
-        d = per.setdefault(name, [0, 0.0, 0.0])
-        t = a.elapsed_time(b)
-        d[0] += 1; d[1] += t; d[2] += work
-        dump.append((name, t, work))
-    if os.environ.get("BENCH_DUMP_LAUNCHES") and rank == 0:     # per-launch (entry point, ms, algorithmic flops) of the profiled step
-        with open(os.environ["BENCH_DUMP_LAUNCHES"], "w") as f:
-            json.dump([{"name": n, "ms": round(t, 4), "work": w, "args": list(_lib.Stats.args_log[i]) if i < len(_lib.Stats.args_log) else None}
-                       for i, (n, t, w) in enumerate(dump)], f)
+    # one profiled step: CUDA events around every library launch (issued eagerly so that every launch can be bracketed)
+    per, dump, prof_total_ms = {}, [], 0.0
+    if args.workload != "dmd" or not graphed:
+        _lib.Stats.reset()
+        _lib.Stats.work_fn = _work
+        _lib.Stats.timing = True
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        saved = getattr(tr, "_section", None)
+        if graphed:
+            tr._section = None
+        pe0.record()
+        tr.step(resident[0])
+        pe1.record()
+        torch.cuda.synchronize()
+        if graphed:
+            tr._section = saved
+        _lib.Stats.timing = False
+        prof_total_ms = pe0.elapsed_time(pe1)
+        for name, a, b, work in _lib.Stats.events:
+            d = per.setdefault(name, [0, 0.0, 0.0])
+            t = a.elapsed_time(b)
+            d[0] += 1; d[1] += t; d[2] += work
+            dump.append((name, t, work))
+        if os.environ.get("BENCH_DUMP_LAUNCHES") and rank == 0:     # per-launch (entry point, ms, algorithmic flops) of the profiled step
+            with open(os.environ["BENCH_DUMP_LAUNCHES"], "w") as f:
+                json.dump([{"name": n, "ms": round(t, 4), "work": w, "args": list(_lib.Stats.args_log[i]) if i < len(_lib.Stats.args_log) else None}
+                           for i, (n, t, w) in enumerate(dump)], f)
     step_ms_prof = prof_total_ms          # whole profiled step on the device (library kernels + the PyTorch ones)
     lib_ms = sum(v[1] for v in per.values())
+    del tr
+    torch.cuda.empty_cache()
+
+    # secondary legs (every rank takes part in the ones that exchange)
+    extra = {}
+    if args.workload == "tokenizer" and not args.no_dmd_stage:
+        extra["dmd_stage"] = measure_dmd_stage(dev, world, rank, B)
+    if args.workload == "tokenizer" and args.parity_steps > 0:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import loss_parity
+        lp_out = loss_parity.run_parity(dev, steps=args.parity_steps, global_batch=16, size="large", cuda_graph=True)
+        torch.cuda.empty_cache()
+        if rank == 0:
+            extra["loss_parity"] = lp_out
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
     peaks = load_peaks()
@@ -330,6 +482,7 @@ def run_ours(args):
     roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, fwd + dgrad launches)",
             "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
             "frac": round(achieved / peaks["tf_sustained"], 4), "peak_source": f"{peaks['src']} (sustained: kernel timed inside a long step)",
+            "frac_of_burst_peak": round(achieved / peaks["tf_burst"], 4), "burst_peak": peaks["tf_burst"],
             "launches_per_step": tc[0], "avg_launch_ms": round(tc[1] / max(tc[0], 1), 4),
             "flops_per_launch_avg": tc[2] / max(tc[0], 1), "traffic": None,
             "share_of_step": round(tc[1] / max(step_ms_prof, 1e-9), 4)}
@@ -341,18 +494,9 @@ def run_ours(args):
         "metric": METRIC, "value": round(imgs / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": {
-            "tokenizer": "train_tokenizer.py VAE pretrain step (BASELINE configs[1]): frozen ViT-L/16 encoder, flux Decoder "
-                         "fwd+bwd, L1+LPIPS(VGG16), allreduce, clip, AdamW, EMA",
-            "stress512": "BASELINE configs[4] stress: flux_ae Encoder -> reparam+KL -> Decoder fwd+bwd at 512x512, L1 + KL, "
-                         "allreduce, clip, AdamW, EMA",
-            "dmd": "train_dmd.py iteration (BASELINE configs[2]): LightningDiT-Mini/1 teacher+student; every 5th iteration is a VAE "
-                   "turn (trainable ViT-L/16 encoder + flux Decoder fwd+bwd, L1+LPIPS+10*DMD cfg 5), every iteration a student "
-                   "flow-matching step; allreduce, clip, AdamW per network; steps rounded up to whole 5-iteration cycles"}[args.workload],
-                   "per_gpu_batch": B, "global_batch": B * world,
-                   "image": f"3x{res}x{res}", "z_channels": 16 if args.workload == "stress512" else 32, "parallelism": f"dp{world}",
-                   "weights": "random init (seed 42)", "cuda_graph": graphed,
-                   "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; 4 rotating input batches"},
+        "config": workload_config(args.workload, B, world, res),
+        "run": {"cuda_graph": graphed, "gradient_exchange": exchange_mode,
+                "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; 4 rotating input batches"},
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": B * 3 * res * res * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last.get("loss")},
         "gpu_launches": launches, "host_issue_ms_per_step": round(host_issue_ms, 3), "clocks": clocks, "roofline": roof,
@@ -361,10 +505,17 @@ def run_ours(args):
         "profiled_step_ms": {"total": round(prof_total_ms, 3), "library_kernels": round(lib_ms, 3)},
         "kernels_ms_per_step": kernels,
     }
-    if world == 1 and not args.no_cpu_baseline and args.workload == "tokenizer":
-        out["cpu_baseline"] = cpu_step_baseline(sample_images=1, reps=1)
+    out.update(extra)
+    if args.workload == "tokenizer":
+        out["roofline_hbm"] = measure_dmd_kernel_roofline(dev, peaks)
+        torch.cuda.empty_cache()
+        if world == 1 and not args.no_gpu_baseline:
+            out["gpu_baseline"] = measure_gpu_baseline(dev, B)
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_step_baseline(sample_images=1, reps=1)
     emit(out)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -434,11 +585,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "train_tokenizer.py VAE pretrain step (BASELINE configs[1]) on the host cores: oracle port of the "
-                               "reference's PyTorch modules (the Python reference itself does not travel to the GPU box)",
-                   "per_step_batch": b, "image": "3x256x256", "z_channels": 32},
+        "config": workload_config("tokenizer", args.batch, int(os.environ.get("WORLD_SIZE", 1)), 256),
+        "run": {"arm": "the workload's step on the host cores: oracle port of the reference's PyTorch modules, fp32 (the Python "
+                       "reference itself does not travel to the GPU box)", "images_per_sampled_step": b},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of {b} image(s) after {args.warmup} warm-up"},
+                         "sample": f"{args.steps} steps after {args.warmup} warm-up, each a bounded sample of {b} image(s) of the "
+                                   f"{args.batch}-image batch, fp32, torch.set_num_threads({cores})"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "last_loss": loss})
 
@@ -473,6 +625,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock PyTorch/cuDNN eager step (N=1 only)")
+    ap.add_argument("--no-dmd-stage", action="store_true", help="skip the secondary train_dmd.py-iteration measurement")
+    ap.add_argument("--parity-steps", type=int, default=100,
+                    help="steps of the loss-parity leg (real trainer vs fp32 anchor vs cuDNN-autocast control); 0 = skip")
+    ap.add_argument("--quick", action="store_true", help="main timing only: no dmd_stage / loss_parity / gpu_baseline / cpu_baseline")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                     help="tokenizer workload: issue every kernel from Python instead of replaying forward+backward from a CUDA graph")
     ap.add_argument("--workload", default="tokenizer", choices=["tokenizer", "stress512", "dmd"],
@@ -483,6 +640,9 @@ def main():
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
+    if args.quick:
+        args.no_cpu_baseline = args.no_gpu_baseline = args.no_dmd_stage = True
+        args.parity_steps = 0
     run_ours(args)
 
 

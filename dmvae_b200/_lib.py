@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvae_b200.so")
 
 F32, BF16 = 0, 1
+ABI_VERSION = 1          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> argtypes  (every function returns int except dmvae_last_error)
@@ -83,6 +84,10 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = argtypes
+        have = lib.dmvae_abi_version()
+        if have != ABI_VERSION:
+            raise DmvaeError(f"{LIB_PATH} exports ABI version {have}, this package binds version {ABI_VERSION}: "
+                             "rebuild with `python -m dmvae_b200.build --force`")
         _lib = lib
     return _lib
 

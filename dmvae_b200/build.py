@@ -13,12 +13,29 @@ NVCC_FLAGS = [
 ]
 
 
+STAMP = os.path.join(HERE, "libdmvae_b200.srchash")
+
+
+def _source_hash() -> str:
+    """sha256 over the CUDA sources, the public header and the compiler flags.  Content, not mtimes: the snapshot that carries the
+    built library to the GPU box does not preserve file times, and a spurious rebuild there would burn GPU minutes."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    files.append(os.path.join(os.path.dirname(HERE), "include", "dmvae_b200.h"))
+    for f in files:
+        if os.path.isfile(f):
+            h.update(os.path.basename(f).encode())
+            with open(f, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as fh:
+        return fh.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -43,6 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
     cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB, *objs]
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as fh:
+        fh.write(_source_hash())
     return LIB
 
 

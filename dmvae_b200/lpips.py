@@ -15,6 +15,7 @@ import torch
 from torch import nn
 
 from . import ops
+from ._lib import DmvaeError
 from .losses import lpips_tap_distance
 
 _VGG_PLAN = [  # torchvision vgg16.features indices: (idx, kind, cin, cout)
@@ -75,21 +76,6 @@ class vgg16(nn.Module):
             outs.append(h)
         return outs
 
-    def _frozen_operands(self, dtype):
-        """Conv weights in `dtype`, channels-last, cached across steps (the net is frozen): saves the per-call
-        fp32->bf16 autocast casts and cuDNN's NCHW->NHWC filter transposes."""
-        key = (dtype, tuple(p._version for p in self.parameters()), next(self.parameters()).device)
-        cache = self.__dict__.get("_wcache")
-        if cache is None or cache[0] != key:
-            ops_ = {}
-            for name, m in self.named_modules():
-                if isinstance(m, nn.Conv2d):
-                    ops_[name] = (m.weight.detach().to(dtype).contiguous(memory_format=torch.channels_last),
-                                  m.bias.detach().to(dtype))
-            cache = (key, ops_)
-            self.__dict__["_wcache"] = cache
-        return cache[1]
-
     def forward_b200(self, X):
         """Frozen-weight VGG16 pass on the library's own conv tiles: channels-last bf16 activations,
         tcgen05 implicit-GEMM convs (thin-input kernel for the 3->64 stem), same bf16/fp32 rounding points as the
@@ -110,22 +96,6 @@ class vgg16(nn.Module):
                 else:
                     h = nn.functional.max_pool2d(h.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
             outs.append(h.permute(0, 3, 1, 2))                        # NCHW-logical view of the channels-last buffer
-        return outs
-
-    def forward_frozen(self, X, dtype):
-        """Same graph as forward() for frozen weights, X already channels-last in `dtype`."""
-        w = self._frozen_operands(dtype)
-        outs, h = [], X
-        for k in range(1, 6):
-            for name, m in getattr(self, f"slice{k}").named_children():
-                if isinstance(m, nn.Conv2d):
-                    wt, b = w[f"slice{k}.{name}"]
-                    h = nn.functional.conv2d(h, wt, b, padding=1)
-                elif isinstance(m, nn.ReLU):
-                    h = torch.relu(h)
-                else:
-                    h = nn.functional.max_pool2d(h, 2, 2)
-            outs.append(h)
         return outs
 
 
@@ -154,13 +124,12 @@ class NetLinLayer(nn.Module):
 
 
 class LPIPS(nn.Module):
-    def __init__(self, ckpt_path=None, use_dropout=True, pretrained_vgg=True, faithful=None, vgg_backend="b200"):
+    def __init__(self, ckpt_path=None, use_dropout=True, pretrained_vgg=True, faithful=None):
         """faithful: reproduce the bf16 roundings autocast puts around the 1x1 lin conv and the bf16 tail
         (None = do so exactly when autocast(bf16) is active, as the reference run would).
-        vgg_backend: "b200" runs the frozen VGG16 convs on this library's tcgen05 tiles under autocast(bf16);
-        "cudnn" keeps them on cuDNN (the reference's path)."""
+        The VGG16 trunk always runs on this library's tcgen05 conv tiles (bf16 operands, fp32 accumulation -- the arithmetic of
+        the reference's autocast run, train_dmd.py:516); there is no cuDNN or CPU variant of the forward pass."""
         super().__init__()
-        self.vgg_backend = vgg_backend
         self.scaling_layer = ScalingLayer()
         self.chns = [64, 128, 256, 512, 512]
         self.net = vgg16(pretrained=pretrained_vgg, requires_grad=False)
@@ -186,24 +155,14 @@ class LPIPS(nn.Module):
         faithful = self.faithful
         if faithful is None:
             faithful = torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
-        cl = torch.channels_last
-        frozen = not any(p.requires_grad for p in self.net.parameters())
-        if frozen and input.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16 \
-                and self.vgg_backend == "b200":
-            with torch.autocast("cuda", enabled=False):
-                with torch.no_grad():
-                    f0 = self.net.forward_b200(self.scaling_layer(input.float()))
-                f1 = self.net.forward_b200(self.scaling_layer(target.float()))
-        elif frozen and input.is_cuda and torch.is_autocast_enabled():
-            dt = torch.get_autocast_dtype("cuda")
-            with torch.autocast("cuda", enabled=False):
-                with torch.no_grad():
-                    f0 = self.net.forward_frozen(self.scaling_layer(input).to(dt).contiguous(memory_format=cl), dt)
-                f1 = self.net.forward_frozen(self.scaling_layer(target).to(dt).contiguous(memory_format=cl), dt)
-        else:
+        if not input.is_cuda:
+            raise DmvaeError(f"LPIPS: input is on {input.device}; dmvae_b200 has no CPU path")
+        if any(p.requires_grad for p in self.net.parameters()):
+            raise DmvaeError("LPIPS: the VGG16 trunk is frozen on this path (utils/lpips.py:119-121 requires_grad=False)")
+        with torch.autocast("cuda", enabled=False):
             with torch.no_grad():
-                f0 = self.net(self.scaling_layer(input).contiguous(memory_format=cl))
-            f1 = self.net(self.scaling_layer(target).contiguous(memory_format=cl))
+                f0 = self.net.forward_b200(self.scaling_layer(input.float()))
+            f1 = self.net.forward_b200(self.scaling_layer(target.float()))
         val = None
         for k in range(5):
             w = getattr(self, f"lin{k}").weight

@@ -6,6 +6,10 @@ Replaces, for the trainable VAE parameters, the reference's per-step sequence
 and the EMA copy each live in one flat fp32 buffer; the ``nn.Parameter``s stay ordinary parameters whose ``.data`` / ``.grad``
 are views into those buffers, so ``state_dict()``, ``load_state_dict()`` (in-place copy), DDP-free all-reduce (GradArena)
 and the packed-weight caches (version counters are bumped after every step) keep working.
+
+Checkpointing follows the reference's entries (train_tokenizer.py:439-453: ``opt_vae`` and a full ``vae_ema`` state_dict):
+``state_dict()`` / ``load_state_dict()`` carry the moments, the step count and the EMA arena; ``ema_state_dict(module)`` merges
+the EMA views with the module's frozen parameters and buffers into a dict that ``VAE.load_pretrained(ema=True)`` loads strictly.
 """
 from __future__ import annotations
 
@@ -44,10 +48,21 @@ class FlatAdamWEMA:
         self.t = 0
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._ema_synced_at = tuple(p._version for p in self.params)
+
+    def sync_ema(self) -> None:
+        """EMA := current weights.  The reference deep-copies the model into ``vae_ema`` after the weights are in place
+        (train_tokenizer.py:397); call this after ``load_state_dict`` / ``load_pretrained`` on a model whose trainer already
+        exists.  ``step()`` does it by itself when it sees, before the first update, that the weights changed since construction."""
+        if self.ema is not None:
+            self.ema.copy_(self.flat_p)
+        self._ema_synced_at = tuple(p._version for p in self.params)
 
     @torch.no_grad()
     def step(self, lr: Optional[float] = None) -> torch.Tensor:
         """One optimizer step on the gradients currently in the arena.  Returns the pre-clip gradient norm (0-d, device)."""
+        if self.t == 0 and self.ema is not None and tuple(p._version for p in self.params) != self._ema_synced_at:
+            self.sync_ema()                             # weights were loaded after the trainer was built
         self.t += 1
         n = self.flat_p.numel()
         self._sumsq.zero_()
@@ -58,6 +73,7 @@ class FlatAdamWEMA:
         torch.autograd.graph.increment_version(self.params)      # the kernel wrote through raw pointers
         return self._norm[0]
 
+    # ------------------------------------------------------------------------------------------------ EMA views / checkpoints
     def ema_state(self, named_params: Dict[str, nn.Parameter]) -> Dict[str, torch.Tensor]:
         """EMA tensors keyed like ``named_parameters()`` (the trainable part of the reference's ``vae_ema`` checkpoint entry)."""
         out, off = {}, 0
@@ -67,3 +83,38 @@ class FlatAdamWEMA:
                 out[by_id[id(p)]] = self.ema[off:off + p.numel()].view_as(p)
             off += p.numel()
         return out
+
+    def ema_state_dict(self, module: nn.Module) -> Dict[str, torch.Tensor]:
+        """A full reference-format ``vae_ema`` entry (train_tokenizer.py:441): ``module.state_dict()`` with every trainable
+        tensor replaced by its EMA value; frozen parameters (the stage-1 encoder) and buffers are the live ones, exactly what
+        ``update_ema`` leaves in the reference's deep-copied model (train_tokenizer.py:140-150 only touches requires_grad
+        parameters).  Loads with ``strict=True``."""
+        sd = {k: v.detach().clone() for k, v in module.state_dict().items()}
+        for k, v in self.ema_state(dict(module.named_parameters())).items():
+            sd[k] = v.detach().clone()
+        return sd
+
+    def state_dict(self) -> Dict[str, object]:
+        """The ``opt_vae`` checkpoint entry: moments, step count, hyper-parameters and the EMA arena (flat, in arena order;
+        ``numel`` / ``shapes`` guard against loading into a different parameter set)."""
+        return {"step": self.t, "exp_avg": self.m.detach().clone(), "exp_avg_sq": self.v.detach().clone(),
+                "ema": None if self.ema is None else self.ema.detach().clone(),
+                "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "max_norm": self.max_norm,
+                "ema_decay": self.ema_decay, "shapes": [tuple(p.shape) for p in self.params]}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        shapes = [tuple(s) for s in sd["shapes"]]
+        if shapes != [tuple(p.shape) for p in self.params]:
+            raise ValueError("FlatAdamWEMA.load_state_dict: parameter shapes differ from the checkpoint's")
+        with torch.no_grad():
+            self.m.copy_(sd["exp_avg"])
+            self.v.copy_(sd["exp_avg_sq"])
+            if self.ema is not None:
+                if sd.get("ema") is not None:
+                    self.ema.copy_(sd["ema"])
+                else:
+                    self.ema.copy_(self.flat_p)
+        self.t = int(sd["step"])
+        self.lr, self.betas, self.eps, self.wd = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
+        self.max_norm = float(sd["max_norm"])
+        self._ema_synced_at = tuple(p._version for p in self.params)

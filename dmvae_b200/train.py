@@ -1,16 +1,17 @@
 """Host-side training step for the hot path: the reference's ``VAELossFunction`` surface (train_dmd.py:169-262,
 train_tokenizer.py:153-199) on the fused kernels, a flat gradient arena with one NCCL allreduce per step (the DDP
-exchange of train_dmd.py:348 / train_tokenizer.py:302), and a small trainer used by bench.py and the tests.
+exchange of train_dmd.py:348 / train_tokenizer.py:302), and the two trainers used by bench.py and the tests.
 
 Discriminator / GAN branches are out of scope (stock PyTorch in the reference, not on this path).
+There is no PyTorch-optimizer or CPU variant of the trainers: they need CUDA parameters and the library's fused
+clip + AdamW (+ EMA) kernels (``optim.FlatAdamWEMA``).
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, Dict, Iterable, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
-import torch.distributed as tdist
 from torch import nn
 
 from . import losses
@@ -18,16 +19,25 @@ from .vae import latents_to_spatial
 
 
 # ------------------------------------------------------------------------------------------------ transport glue
+def sample_t(batch: int, like: torch.Tensor, t0: float = 0.0, t1: float = 1.0,
+             cpu_generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """t ~ U(t0, t1) drawn on the CPU generator, then moved to ``like``'s device and dtype -- so t is bf16 when the latents are
+    (diffusion/transport/transport.py:111-114)."""
+    return (torch.rand((batch,), generator=cpu_generator) * (t1 - t0) + t0).to(like)
+
+
+def shift_t(t: torch.Tensor, time_dist_shift: float) -> torch.Tensor:
+    """The time-distribution shift of Transport.sample (transport.py:115)."""
+    return 1 - time_dist_shift * (1 - t) / (1 + (time_dist_shift - 1) * (1 - t))
+
+
 def sample_t_x0(x1: torch.Tensor, time_dist_shift: float = 1.0, t0: float = 0.0, t1: float = 1.0,
                 cpu_generator: Optional[torch.Generator] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Transport.sample (diffusion/transport/transport.py:105-116) for the linear / velocity plan:
     x0 ~ N(0, I) from the device generator, t ~ U(t0, t1) drawn on the CPU generator then moved to x1's device and
-    dtype (so t is bf16 when the latents are), followed by the time-distribution shift."""
+    dtype, followed by the time-distribution shift."""
     x0 = torch.randn_like(x1)
-    t = torch.rand((x1.shape[0],), generator=cpu_generator) * (t1 - t0) + t0
-    t = t.to(x1)
-    t = 1 - time_dist_shift * (1 - t) / (1 + (time_dist_shift - 1) * (1 - t))
-    return t, x0
+    return shift_t(sample_t(x1.shape[0], x1, t0, t1, cpu_generator), time_dist_shift), x0
 
 
 @dataclass
@@ -60,11 +70,16 @@ class VAELossFunction:
                                            cpu_generator: Optional[torch.Generator] = None,
                                            t: Optional[torch.Tensor] = None, x0: Optional[torch.Tensor] = None):
         """train_dmd.py:204-230.  Returns (loss, log) with device-side scalars in ``log`` (no host sync here).
-        ``t`` / ``x0`` may be injected (what ``self.transport.sample`` returns in the reference) for reproducible tests."""
+        ``t`` / ``x0`` may be injected (what ``self.transport.sample`` returns in the reference): tests use it for
+        reproducibility, the CUDA-graph trainer to feed the CPU-drawn t through a static device buffer."""
         a = self.args
-        if t is None or x0 is None:
-            t, x0 = sample_t_x0(latents_norm, a.time_dist_shift, cpu_generator=cpu_generator)
+        if x0 is None:
+            x0 = torch.randn_like(latents_norm)
+        if t is None:
+            t = shift_t(sample_t(latents_norm.shape[0], latents_norm, cpu_generator=cpu_generator), a.time_dist_shift)
         t = t * (a.t1 - a.t0) + a.t0
+        if isinstance(self.base_model, nn.Module) and self.base_model.training:
+            raise RuntimeError("DMD teacher must be in eval mode (train_dmd.py:372): a train-mode LightningDiT drops labels at random")
         xt = losses.dmd_mix_xt(latents_norm, x0, t)
         with torch.no_grad():
             vT_u = vS_u = None
@@ -84,7 +99,7 @@ class VAELossFunction:
         loss, gnorm = losses.dmd_loss(latents_norm, xt, t, v_teacher, v_student, vT_u, vS_u, a.dmd_cfg_scale, True)
         return loss, {"dmd_loss": loss.detach(), "dmd_gradient_norm": gnorm}
 
-    def forward_generator(self, images_pm1, recon_image, latents=None, labels=None, compute_dmd=False, step=0):
+    def forward_generator(self, images_pm1, recon_image, latents=None, labels=None, compute_dmd=False, step=0, t=None):
         """train_dmd.py:233-262 without the discriminator branch."""
         l1, l2 = losses.l1_l2_loss(recon_image, images_pm1)
         rec_loss = l1 * self.l1 + l2 * self.l2
@@ -95,7 +110,7 @@ class VAELossFunction:
             log["LPIPS"] = lp.detach()
         log["rec_loss"] = rec_loss.detach()
         if compute_dmd:
-            dmd, dmd_log = self.compute_distribution_matching_loss(latents, labels, step)
+            dmd, dmd_log = self.compute_distribution_matching_loss(latents, labels, step, t=t)
             log.update(dmd_log)
             rec_loss = rec_loss + dmd * self.dmd_weight
         return rec_loss, log
@@ -105,175 +120,293 @@ from .train_arena import GradArena  # noqa: E402,F401  (re-exported)
 
 
 def dit_training_loss(model: Callable, latents: torch.Tensor, labels: torch.Tensor, time_dist_shift: float = 1.0,
-                      cpu_generator: Optional[torch.Generator] = None) -> torch.Tensor:
+                      cpu_generator: Optional[torch.Generator] = None, t: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Transport.training_losses for the linear path / velocity prediction (diffusion/transport/transport.py:119-142):
-    xt = t*x1 + (1-t)*x0, target ut = x1 - x0, loss = mean over batch of the per-sample mean squared error."""
-    t, x0 = sample_t_x0(latents, time_dist_shift, cpu_generator=cpu_generator)
+    xt = t*x1 + (1-t)*x0, target ut = x1 - x0, loss = mean over batch of the per-sample mean squared error.
+    ``t`` (already shifted) may be injected, see compute_distribution_matching_loss."""
+    x0 = torch.randn_like(latents)
+    if t is None:
+        t = shift_t(sample_t(latents.shape[0], latents, cpu_generator=cpu_generator), time_dist_shift)
     xt = losses.dmd_mix_xt(latents, x0, t)
     ut = latents - x0
     out = model(xt, t, labels)
     return ((out - ut) ** 2).flatten(1).mean(1).mean()
 
 
-@torch.no_grad()
-def update_ema(ema_params: List[torch.Tensor], params: List[torch.Tensor], decay: float = 0.9999):
-    """train_tokenizer.py:140-150 as two foreach passes."""
-    torch._foreach_mul_(ema_params, decay)
-    torch._foreach_add_(ema_params, params, alpha=1 - decay)
+# ------------------------------------------------------------------------------------------------ CUDA-graph sections
+class GraphCaptureError(RuntimeError):
+    pass
+
+
+class _GraphedSection:
+    """``fn()`` (no arguments, fixed shapes, reads its inputs from static buffers) captured once into a CUDA graph.
+
+    Capture protocol: warm up on a side stream (kernel attributes, tensor maps, cuBLAS / cuDNN plans, NCCL channels), bump
+    the parameters' version counters so the bf16 operand re-packs are part of what gets captured, capture, then replay once so
+    that every buffer the capture allocated in the graph's private pool holds real data (an eager pass right after the capture
+    would otherwise see an unchanged version counter and read packs that were only *recorded*, never written)."""
+
+    def __init__(self, fn: Callable[[], Dict[str, torch.Tensor]], params: List[nn.Parameter], warmup: int = 2):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if params:
+            torch.autograd.graph.increment_version(params)
+        self.graph = torch.cuda.CUDAGraph()
+        # with a process group alive its watchdog thread polls CUDA events concurrently: only this thread's calls belong to the capture
+        mode = "thread_local" if GradArena._distributed() else "global"
+        with torch.cuda.graph(self.graph, capture_error_mode=mode):
+            self.out = fn()
+        self.graph.replay()
+        torch.cuda.synchronize()
+
+    def replay(self) -> Dict[str, torch.Tensor]:
+        self.graph.replay()
+        return dict(self.out)
+
+
+def _capture_with_exchange(fn: Callable[[], Dict[str, torch.Tensor]], arenas: List[GradArena], params: List[nn.Parameter],
+                           warmup: int) -> Tuple[_GraphedSection, str]:
+    """Capture ``fn`` (which ends with ``arena.allreduce()``) with the chunked NCCL all-reduces INSIDE the graph: the hooks fire
+    during the captured backward, each collective lands on NCCL's stream as a forked branch of the graph and overlaps the
+    rest of backward on every replay.  If the process group cannot be captured, fall back to a graph without the exchange
+    (hooks off; the caller issues ``arena.allreduce()`` after each replay).  Returns (section, "in-graph" | "post-replay")."""
+    distributed = GradArena._distributed()
+    if not distributed:
+        return _GraphedSection(fn, params, warmup), "none"
+    try:
+        return _GraphedSection(fn, params, warmup), "in-graph"
+    except Exception as e:                              # noqa: BLE001
+        import warnings
+        warnings.warn(f"NCCL exchange could not be captured ({type(e).__name__}: {e}); capturing without it")
+        torch.cuda.synchronize()
+    for a in arenas:
+        a.hooks_enabled = False
+        a.begin_step()
+    return _GraphedSection(fn, params, warmup), "post-replay"
 
 
 class TokenizerTrainer:
     """One VAE-pretrain step of train_tokenizer.py:403-437 (frozen encoder, recon losses, clip, AdamW, EMA)."""
 
     def __init__(self, vae: nn.Module, loss_fn: VAELossFunction, lr: float = 1e-4, wd: float = 0.0, ema: bool = True,
-                 clip: float = 1.0, fused_optimizer: bool = True):
+                 clip: float = 1.0):
+        from .optim import FlatAdamWEMA
         self.vae = vae
         self.loss_fn = loss_fn
         self.clip = clip
         self.arena = GradArena(vae.parameters())
         self.params = self.arena.params
-        self.fused = None
-        if fused_optimizer and self.params[0].is_cuda:
-            from .optim import FlatAdamWEMA
-            self.fused = FlatAdamWEMA(self.params, lr=lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd, max_norm=clip,
-                                      ema_decay=0.9999 if ema else None, arena=self.arena)
-            self.opt, self.ema = None, None
-            return
-        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=wd, betas=(0.9, 0.95), eps=1e-8, fused=self.params[0].is_cuda)
-        self.ema = [p.detach().clone() for p in self.params] if ema else None
+        self.fused = FlatAdamWEMA(self.params, lr=lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd, max_norm=clip,
+                                  ema_decay=0.9999 if ema else None, arena=self.arena)
+        self._section: Optional[_GraphedSection] = None
+        self._exchange_outside = True       # eager: _forward_backward ends with the exchange itself
+        self.exchange_mode = "eager"
 
-    def _forward_backward(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def _forward_backward(self, images: torch.Tensor, exchange: bool = True) -> Dict[str, torch.Tensor]:
         self.arena.zero()
         with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
             recon = self.vae(images, freeze_encoder=True)
             loss, log = self.loss_fn.forward_generator(images, recon)
         with self.arena.direct():                   # conv / GroupNorm gradients accumulate straight into the arena
             loss.backward()
+        if exchange:
+            self.arena.allreduce()                  # chunks not yet launched from the hooks, wait, (average inside NCCL)
         log["loss"] = loss.detach()
         return log
 
-    def capture_cuda_graph(self, example_images: torch.Tensor, warmup: int = 2) -> bool:
-        """Capture forward + backward of one step (≈1100 kernel launches at fixed shapes) into a CUDA graph; ``step`` then copies
-        the batch into the graph's input buffer and replays it, leaving only the gradient exchange and the two optimizer
-        kernels (whose step count / learning rate are host-side scalars) to be issued from Python.  With several ranks the NCCL
-        exchange is issued after the replay (0.5 ms for 207 MB over NVLink, not overlapped).  Returns False -- and stays eager --
-        if capture fails."""
-        if self.fused is None or not example_images.is_cuda:
-            return False
-        self._graph = None
-        self.arena.hooks_enabled = False            # nothing may enqueue a collective from inside the captured backward
+    def capture_cuda_graph(self, example_images: torch.Tensor, warmup: int = 2, strict: bool = False) -> bool:
+        """Capture forward + backward + gradient exchange of one step (≈1100 kernel launches at fixed shapes) into a CUDA
+        graph; ``step`` then copies the batch into the graph's input buffer and replays it, leaving only the two optimizer
+        kernels (whose step count / learning rate are host-side scalars) to be issued from Python.  With several ranks the
+        chunked NCCL all-reduces are captured too (forked onto NCCL's stream from the hooks, so they overlap the rest of
+        backward in every replay); ``exchange_mode`` says whether that worked ("in-graph") or the exchange runs after each
+        replay ("post-replay").  ``strict``: raise GraphCaptureError instead of returning False when capture fails."""
+        self._section = None
+        self.arena.hooks_enabled = True
         try:
             self._gx = example_images.clone()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):           # warm up off the default stream: kernel attributes, tensor maps, cuDNN / cuBLAS plans
-                for _ in range(max(1, warmup)):
-                    self._forward_backward(self._gx)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            # the bf16 operand packs are refreshed only when a parameter's version counter moved: make sure the refresh is part
-            # of what gets captured, so that every replay re-packs the weights the optimizer has just updated
-            torch.autograd.graph.increment_version(self.params)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._glog = self._forward_backward(self._gx)
-            self._graph = graph
+
+            def body():                             # hooks off (fallback capture) = the exchange is issued after each replay
+                return self._forward_backward(self._gx, exchange=self.arena.hooks_enabled)
+            self._section, self.exchange_mode = _capture_with_exchange(body, [self.arena], self.params, warmup)
+            self._exchange_outside = self.exchange_mode == "post-replay"
             return True
-        except Exception as e:                      # noqa: BLE001 -- any capture problem means: keep the eager path
+        except Exception as e:                      # noqa: BLE001
+            self._section = None
+            self.arena.hooks_enabled = True
+            self.exchange_mode = "eager"
+            torch.cuda.synchronize()
+            if strict:
+                raise GraphCaptureError(f"TokenizerTrainer: CUDA graph capture failed ({type(e).__name__}: {e})") from e
             import warnings
             warnings.warn(f"TokenizerTrainer: CUDA graph capture failed ({type(e).__name__}: {e}); staying eager")
-            self._graph = None
-            self.arena.hooks_enabled = True
-            torch.cuda.synchronize()
             return False
 
+    @property
+    def graphed(self) -> bool:
+        return self._section is not None
+
     def step(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
-        if getattr(self, "_graph", None) is not None and images.shape == self._gx.shape:
+        if self._section is not None and images.shape == self._gx.shape:
             self._gx.copy_(images, non_blocking=True)
-            self._graph.replay()
-            log = dict(self._glog)
+            log = self._section.replay()
+            if self._exchange_outside:
+                self.arena.allreduce()
         else:
             log = self._forward_backward(images)
-        loss = log["loss"]
-        self.arena.allreduce()
-        if self.fused is not None:                  # clip + AdamW + EMA in two kernels over the flat arenas
-            log["vae_norm"] = self.fused.step()
-            return log
-        # clip_grad_norm_(params, 1.0) (train_tokenizer.py:415) on the flat arena: one norm, one scale
-        total = torch.linalg.vector_norm(self.arena.flat, 2)
-        self.arena.flat.mul_(torch.clamp(self.clip / (total + 1e-6), max=1.0))
-        log["vae_norm"] = total
-        self.opt.step()
-        if self.ema is not None:
-            update_ema(self.ema, [p.data for p in self.params])
-        log["loss"] = loss.detach()
+        log["vae_norm"] = self.fused.step()         # clip + AdamW + EMA in two kernels over the flat arenas
         return log
 
 
 class DmdTrainer:
     """One train_dmd.py iteration (:506-575) without the discriminator: the VAE turn (whole VAE trainable incl. the encoder,
-    :519; recon + LPIPS + dmd_weight * DMD; clip; AdamW) followed by the student-DiT flow-matching step (:563-575)."""
+    :519; recon + LPIPS + dmd_weight * DMD; clip; AdamW) followed by the student-DiT flow-matching step (:563-575).
+
+    ``capture_cuda_graphs`` turns the iteration into three replayed graphs -- VAE turn (forward, 4 DiT forwards batched as 2,
+    fused DMD loss, backward, exchange), encode-only (the other iterations, :522-524) and the student step -- that hand the
+    latents to each other through a static buffer; the CPU-drawn diffusion times (transport.py:111-114) travel through two
+    small static device buffers, and only the fused optimizer kernels are issued from Python."""
 
     def __init__(self, vae: nn.Module, sit: nn.Module, base_model: nn.Module, lpips_loss: Optional[nn.Module], cfg: LossConfig,
                  lr_vae: float = 2e-5, lr_sit: float = 2e-5, latent_mean: float = 0.0, latent_scale: float = 1.0,
-                 wd: float = 0.005, fused_optimizer: bool = True):
+                 wd: float = 0.005, cpu_generator: Optional[torch.Generator] = None):
+        from .optim import FlatAdamWEMA
         self.vae, self.sit, self.base = vae, sit, base_model
         self.cfg, self.latent_mean, self.latent_scale = cfg, latent_mean, latent_scale
         self.loss_fn = VAELossFunction(cfg, lpips_loss=lpips_loss, sit=sit, base_model=base_model)
+        self.cpu_generator = cpu_generator
+        base_model.eval()                               # train_dmd.py:372
         for p in base_model.parameters():
             p.requires_grad = False
         self.arena_vae = GradArena(vae.parameters())
         self.arena_sit = GradArena(sit.parameters())
-        self.fused = fused_optimizer and self.arena_vae.params[0].is_cuda
-        if self.fused:          # clip + AdamW in two kernels per network over the flat arenas (train_dmd.py has no EMA)
-            from .optim import FlatAdamWEMA
-            kw = dict(betas=(0.9, 0.95), eps=1e-8, weight_decay=wd, max_norm=1.0, ema_decay=None)
-            self.opt_vae = FlatAdamWEMA(self.arena_vae.params, lr=lr_vae, arena=self.arena_vae, **kw)
-            self.opt_sit = FlatAdamWEMA(self.arena_sit.params, lr=lr_sit, arena=self.arena_sit, **kw)
-        else:
-            self.opt_vae = torch.optim.AdamW(self.arena_vae.params, lr=lr_vae, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd)
-            self.opt_sit = torch.optim.AdamW(self.arena_sit.params, lr=lr_sit, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd)
+        # clip + AdamW in two kernels per network over the flat arenas (train_dmd.py has no EMA)
+        kw = dict(betas=(0.9, 0.95), eps=1e-8, weight_decay=wd, max_norm=1.0, ema_decay=None)
+        self.opt_vae = FlatAdamWEMA(self.arena_vae.params, lr=lr_vae, arena=self.arena_vae, **kw)
+        self.opt_sit = FlatAdamWEMA(self.arena_sit.params, lr=lr_sit, arena=self.arena_sit, **kw)
+        self._sections: Optional[Dict[str, _GraphedSection]] = None
+        self.exchange_mode = "eager"
 
-    def _clip_step(self, arena: GradArena, opt, max_norm: float = 1.0) -> torch.Tensor:
-        """clip_grad_norm_(params, 1.0); optimizer.step() (train_dmd.py:540-542, :568-570)."""
-        if self.fused:
-            return opt.step()
-        total = torch.linalg.vector_norm(arena.flat, 2)
-        arena.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
-        opt.step()
-        return total
+    # ---- the three pieces of an iteration (each runs eagerly or under capture)
+    def _latents(self, z: torch.Tensor) -> torch.Tensor:
+        return latents_to_spatial((z - self.latent_mean) * self.latent_scale)       # train_dmd.py:525-526
 
-    def step(self, images: torch.Tensor, labels: torch.Tensor, vae_turn: bool = True) -> Dict[str, torch.Tensor]:
-        dev = images.device.type
-        log: Dict[str, torch.Tensor] = {}
+    def _vae_turn(self, images, labels, t_dmd, exchange: bool = True) -> Tuple[Dict[str, torch.Tensor], torch.Tensor]:
+        self.sit.eval()                                 # train_dmd.py:529-531: the student is a frozen scorer in the VAE turn
+        for p in self.sit.parameters():
+            p.requires_grad = False
         self.arena_vae.zero()
-        with torch.autocast(device_type=dev, dtype=torch.bfloat16):
-            if vae_turn:
-                recon, z = self.vae(images, return_latent=True)
-            else:
-                with torch.no_grad():
-                    z = self.vae.encode(images)
-            latents = latents_to_spatial((z - self.latent_mean) * self.latent_scale)
-            if vae_turn:
-                self.sit.eval()
-                for p in self.sit.parameters():
-                    p.requires_grad = False
-                loss, log = self.loss_fn.forward_generator(images, recon, latents, labels, compute_dmd=self.cfg.dmd_weight > 0)
-        if vae_turn:
-            with self.arena_vae.direct():
-                loss.backward()
+        with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
+            recon, z = self.vae(images, return_latent=True)
+            latents = self._latents(z)
+            if t_dmd is None:
+                t_dmd = self._draw_t(latents)
+            loss, log = self.loss_fn.forward_generator(images, recon, latents, labels, compute_dmd=self.cfg.dmd_weight > 0, t=t_dmd)
+        with self.arena_vae.direct():
+            loss.backward()
+        if exchange:
             self.arena_vae.allreduce()
-            log["vae_norm"] = self._clip_step(self.arena_vae, self.opt_vae)
-            log["loss"] = loss.detach()
-        # 2. train the student DiT on the (detached) latents
+        log["loss"] = loss.detach()
+        return log, latents.detach()
+
+    def _encode_only(self, images) -> torch.Tensor:
+        with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16), torch.no_grad():
+            return self._latents(self.vae.encode(images))
+
+    def _sit_step(self, latents, labels, t_sit, exchange: bool = True) -> Dict[str, torch.Tensor]:
         for p in self.sit.parameters():
             p.requires_grad = True
         self.sit.train()
         self.arena_sit.zero()
-        with torch.autocast(device_type=dev, dtype=torch.bfloat16):
-            dloss = dit_training_loss(self.sit, latents.detach(), labels, self.cfg.time_dist_shift)
+        if t_sit is None:
+            t_sit = self._draw_t(latents)
+        with torch.autocast(device_type=latents.device.type, dtype=torch.bfloat16):
+            dloss = dit_training_loss(self.sit, latents, labels, self.cfg.time_dist_shift, t=t_sit)
         dloss.backward()
-        self.arena_sit.allreduce()
-        log["sit_norm"] = self._clip_step(self.arena_sit, self.opt_sit)
-        log["diffusion_loss"] = dloss.detach()
+        if exchange:
+            self.arena_sit.allreduce()
+        return {"diffusion_loss": dloss.detach()}
+
+    def _draw_t(self, like: torch.Tensor) -> torch.Tensor:
+        return shift_t(sample_t(like.shape[0], like, cpu_generator=self.cpu_generator), self.cfg.time_dist_shift)
+
+    # ---- CUDA graphs
+    def capture_cuda_graphs(self, images: torch.Tensor, labels: torch.Tensor, warmup: int = 2, strict: bool = False) -> bool:
+        self._sections = None
+        try:
+            self._gx, self._gy = images.clone(), labels.clone()
+            with torch.no_grad():
+                lat0 = self._encode_only(self._gx)
+            self._glat = lat0.clone()
+            self._gt_dmd = self._draw_t(lat0).clone()
+            self._gt_sit = self._gt_dmd.clone()
+            for a in (self.arena_vae, self.arena_sit):
+                a.hooks_enabled = True
+
+            def turn():
+                log, lat = self._vae_turn(self._gx, self._gy, self._gt_dmd, exchange=self.arena_vae.hooks_enabled)
+                self._glat.copy_(lat)
+                return log
+
+            def enc():
+                self._glat.copy_(self._encode_only(self._gx))
+                return {}
+
+            def sit():
+                return self._sit_step(self._glat, self._gy, self._gt_sit, exchange=self.arena_sit.hooks_enabled)
+            s_turn, m1 = _capture_with_exchange(turn, [self.arena_vae], self.arena_vae.params, warmup)
+            s_enc = _GraphedSection(enc, [], warmup)
+            s_sit, m2 = _capture_with_exchange(sit, [self.arena_sit], self.arena_sit.params, warmup)
+            self._sections = {"turn": s_turn, "enc": s_enc, "sit": s_sit}
+            self._post = {"vae": m1 == "post-replay", "sit": m2 == "post-replay"}
+            self.exchange_mode = m1 if m1 == m2 else f"{m1}/{m2}"
+            return True
+        except Exception as e:                          # noqa: BLE001
+            self._sections = None
+            for a in (self.arena_vae, self.arena_sit):
+                a.hooks_enabled = True
+            self.exchange_mode = "eager"
+            torch.cuda.synchronize()
+            if strict:
+                raise GraphCaptureError(f"DmdTrainer: CUDA graph capture failed ({type(e).__name__}: {e})") from e
+            import warnings
+            warnings.warn(f"DmdTrainer: CUDA graph capture failed ({type(e).__name__}: {e}); staying eager")
+            return False
+
+    @property
+    def graphed(self) -> bool:
+        return self._sections is not None
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor, vae_turn: bool = True) -> Dict[str, torch.Tensor]:
+        log: Dict[str, torch.Tensor] = {}
+        if self._sections is not None and images.shape == self._gx.shape:
+            self._gx.copy_(images, non_blocking=True)
+            self._gy.copy_(labels, non_blocking=True)
+            if vae_turn:
+                self._gt_dmd.copy_(self._draw_t(self._gt_dmd), non_blocking=True)
+                log = self._sections["turn"].replay()
+                if self._post["vae"]:
+                    self.arena_vae.allreduce()
+                log["vae_norm"] = self.opt_vae.step()
+            else:
+                self._sections["enc"].replay()
+            self._gt_sit.copy_(self._draw_t(self._gt_sit), non_blocking=True)
+            log.update(self._sections["sit"].replay())
+            if self._post["sit"]:
+                self.arena_sit.allreduce()
+            log["sit_norm"] = self.opt_sit.step()
+            return log
+        if vae_turn:
+            log, latents = self._vae_turn(images, labels, None)
+            log["vae_norm"] = self.opt_vae.step()       # clip_grad_norm_(1.0); AdamW (train_dmd.py:540-542)
+        else:
+            latents = self._encode_only(images)
+        # 2. train the student DiT on the (detached) latents (train_dmd.py:563-575)
+        log.update(self._sit_step(latents, labels, None))
+        log["sit_norm"] = self.opt_sit.step()
         return log

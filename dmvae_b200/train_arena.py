@@ -14,7 +14,15 @@ class GradArena:
     NVLink/NVSwitch instead of DDP's 25 MB buckets.  With ``overlap=True`` a chunk's all-reduce is issued from an
     autograd hook as soon as every gradient inside it has been accumulated (backward runs output-to-input, so the
     tail of the arena completes first), i.e. the exchange overlaps the rest of the backward pass like DDP's bucketed
-    reduction (train_dmd.py:348).  With world_size == 1 it is just a flat buffer."""
+    reduction (train_dmd.py:348).  With world_size == 1 it is just a flat buffer.
+
+    Step protocol (what a trainer does every step, eagerly or while capturing a CUDA graph):
+        arena.zero()            # clears the buffer AND the per-step exchange bookkeeping
+        loss.backward()         # hooks / notify() launch the chunk all-reduces as chunks complete
+        arena.allreduce()       # launches what is left, waits, averages, resets the bookkeeping
+    ``allreduce()`` leaves the bookkeeping reset, so a loop that never calls ``zero()`` from Python between steps (a
+    replayed CUDA graph only re-runs the captured ``flat.zero_()`` kernel) still exchanges every chunk on every step.
+    On NCCL the average is taken inside the collective (ReduceOp.AVG): no separate division pass."""
 
     def __init__(self, params: Iterable[nn.Parameter], chunks: int = 4, overlap: bool = True):
         self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
@@ -34,12 +42,10 @@ class GradArena:
                 self.bounds.append((start, off))
                 start = off
         self.members = [sum(1 for p in self.params if self.chunk_of[id(p)] == c) for c in range(len(self.bounds))]
-        self._pending = list(self.members)
-        self._handles: List = []
-        self._launched = [False] * len(self.bounds)
         self._slots: Dict[int, torch.Tensor] = {}
-        self._ready = set()
-        self.hooks_enabled = True          # False: no exchange is issued from backward (CUDA-graph replay); allreduce() does it all
+        self.hooks_enabled = True          # False: no exchange is issued from backward; allreduce() does it all
+        self.exchanges = 0                 # chunk all-reduces launched so far (tests / bench accounting)
+        self.begin_step()
         self.overlap = False
         self._attach()
         self.overlap = overlap and self._distributed()
@@ -74,18 +80,25 @@ class GradArena:
         from . import ops
         return ops.direct_param_grads(self)
 
+    def begin_step(self):
+        """Reset the per-step exchange bookkeeping (host side only, no device work)."""
+        self._pending = list(self.members)
+        self._launched = [False] * len(self.bounds)
+        self._handles: List = []
+        self._ready = set()
+
     def zero(self):
         self.flat.zero_()
         self._attach()
-        self._pending = list(self.members)
-        self._launched = [False] * len(self.bounds)
-        self._handles = []
-        self._ready = set()
+        self.begin_step()
 
     def _launch(self, c: int):
         s, e = self.bounds[c]
         self._launched[c] = True
-        self._handles.append(tdist.all_reduce(self.flat[s:e], op=tdist.ReduceOp.SUM, async_op=True))
+        self.exchanges += 1
+        # NCCL averages inside the collective; other backends (gloo in the CPU tests) sum here and divide in allreduce()
+        op = tdist.ReduceOp.AVG if tdist.get_backend() == "nccl" else tdist.ReduceOp.SUM
+        self._handles.append(tdist.all_reduce(self.flat[s:e], op=op, async_op=True))
 
     def _on_grad_ready(self, p: nn.Parameter):
         # once per parameter and step: a Function that accumulated directly reports through notify(), and autograd still
@@ -99,7 +112,7 @@ class GradArena:
             self._launch(c)
 
     def allreduce(self):
-        """Finish the exchange: launch whatever was not launched from hooks, wait, average."""
+        """Finish the exchange: launch whatever was not launched from hooks, wait, average, reset for the next step."""
         if not self._distributed():
             return
         for c in range(len(self.bounds)):
@@ -107,7 +120,6 @@ class GradArena:
                 self._launch(c)
         for h in self._handles:
             h.wait()
-        self._handles = []
-        self.flat.div_(tdist.get_world_size())
-
-
+        if tdist.get_backend() != "nccl":
+            self.flat.div_(tdist.get_world_size())
+        self.begin_step()

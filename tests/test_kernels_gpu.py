@@ -427,6 +427,47 @@ def test_conv_tc_many_tiles_matches_direct():
     assert rel_err(dw_tc, dw_d) < 1e-3
 
 
+@pytest.mark.parametrize("cin,cout,hw,res", [(512, 512, 128, True), (256, 256, 256, True), (128, 128, 256, False), (256, 128, 256, False)])
+def test_conv_production_shapes_at_bench_batch(cin, cout, hw, res):
+    """The decoder's largest layers at the BENCH batch (B = 16): forward with the fused residual, dgrad, and the split-K weight
+    gradient whose contraction runs over K = 16 * hw^2 pixels (up to 1 048 576) with red.global.add fan-in.  Reference: fp32 cuDNN
+    on the same GPU with TF32 off (the CPU oracle needs minutes at this size; torch fp32 is the stated reference for a
+    floating-point kernel).  Tolerances as in _conv_case: bf16 outputs 4e-3, fp32-accumulated weight gradient 1e-3."""
+    ops, _ = _ops()
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        B = 16
+        g = torch.Generator(device=DEV).manual_seed(cin + cout + hw)
+        x = torch.randn(B, hw, hw, cin, generator=g, device=DEV).bfloat16()
+        w = (torch.randn(cout, cin, 3, 3, generator=g, device=DEV) / math.sqrt(9 * cin)).bfloat16().float()
+        b = torch.randn(cout, generator=g, device=DEV)
+        r = torch.randn(B, hw, hw, cout, generator=g, device=DEV).bfloat16() if res else None
+        dy = torch.randn(B, hw, hw, cout, generator=g, device=DEV).bfloat16()
+        wf, wd = ops.WeightPack().get(w)
+        y = ops.conv_forward_raw(x, wf, b, r, 3, 3)
+        dx = ops.conv_dgrad_raw(dy, wf, wd, (hw, hw), 3, 3)
+        dw = ops.conv_wgrad_raw(x, dy, 3, 3)
+        torch.cuda.synchronize()
+        # reference in image chunks (fp32 activations of the whole batch would not be needed at once)
+        dw_ref = torch.zeros_like(w, dtype=torch.float64)
+        for i in range(0, B, 4):
+            xs = x[i:i + 4].float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+            wr = w.clone().requires_grad_(True)
+            yr = F.conv2d(xs, wr, b, padding=1)
+            y_full = yr.detach().bfloat16().float()
+            if res:
+                y_full = (y_full + r[i:i + 4].float().permute(0, 3, 1, 2)).bfloat16().float()
+            yr.backward(dy[i:i + 4].float().permute(0, 3, 1, 2).contiguous())
+            assert rel_err(y[i:i + 4].float().permute(0, 3, 1, 2), y_full) < 4e-3, "forward"
+            assert rel_err(dx[i:i + 4].float().permute(0, 3, 1, 2), xs.grad) < 4e-3, "dgrad"
+            dw_ref += wr.grad.double()
+        assert rel_err(dw, dw_ref) < 1e-3, "wgrad (split-K over the whole batch)"
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
 def test_vit_glue_scale_residual_bit_exact():
     """x += float(y) * gamma must equal the reference's two ATen passes (x + y * gamma with type promotion) bit for bit."""
     from dmvae_b200 import _lib

@@ -146,36 +146,41 @@ def test_retain_graph_partial_grads_and_inference_mode():
     assert rel(y3.float(), 2 * y2.float()) < 1e-2
 
 
-def test_lpips_module_vs_oracle_fp32():
+def test_lpips_module_vs_oracle():
+    """LPIPS module (VGG16 trunk on the tcgen05 tiles, fused distance kernel) vs the oracle.  The trunk always computes with bf16
+    operands / fp32 accumulation (the reference's autocast arithmetic); outside autocast only the tail differs (fp32, no bf16
+    roundings around the 1x1 lin conv).  Tolerance: the reference's own bf16 noise (2^-8 per rounding) -- 3e-2 on the value,
+    5e-2 on the image gradient."""
     from dmvae_b200.lpips import LPIPS
-    torch.backends.cudnn.allow_tf32 = False
     sd = O.make_lpips_state(seed=2)
     lp = LPIPS(ckpt_path=None, pretrained_vgg=False)
-    missing = lp.load_state_dict(sd, strict=True)
+    lp.load_state_dict(sd, strict=True)
     lp = lp.eval().to(DEV)
     g = torch.Generator().manual_seed(3)
     a = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
     b = (a + 0.2 * torch.randn(a.shape, generator=g)).clamp(-1, 1)
+    lin_ws = [sd[f"lin{k}.model.1.weight"].flatten() for k in range(5)]
+    # outside autocast: bf16 trunk, fp32 tail
     br = b.clone().requires_grad_(True)
-    ref = O.lpips_forward(sd, a, br)
+    ref = O.lpips_distance(O.vgg_features(sd, a, True), O.vgg_features(sd, br, True), lin_ws, faithful=False)
     ref.backward()
     bc = b.to(DEV).requires_grad_(True)
     val = lp(a.to(DEV), bc)
     val.backward()
-    assert abs(val.item() - ref.item()) < 1e-3 * abs(ref.item())
-    assert rel(bc.grad, br.grad) < 1e-2
-    # autocast runs (VGG on our tcgen05 tiles, and on cuDNN): within the reference's own bf16 noise (2^-8 per rounding)
+    assert abs(val.item() - ref.item()) < 3e-2 * abs(ref.item())
+    assert rel(bc.grad, br.grad) < 5e-2
+    # under autocast: the reference's bf16 tail as well
     br16 = b.clone().requires_grad_(True)
     ref16 = O.lpips_forward(sd, a, br16, bf16=True)
     ref16.backward()
-    for backend in ("b200", "cudnn"):
-        lp.vgg_backend = backend
-        bc16 = b.to(DEV).requires_grad_(True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            v16 = lp(a.to(DEV), bc16)
-        v16.float().backward()
-        assert abs(v16.float().item() - ref16.item()) < 3e-2 * abs(ref16.item()), backend
-        assert rel(bc16.grad, br16.grad) < 5e-2, backend
+    bc16 = b.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        v16 = lp(a.to(DEV), bc16)
+    v16.float().backward()
+    assert abs(v16.float().item() - ref16.item()) < 3e-2 * abs(ref16.item())
+    assert rel(bc16.grad, br16.grad) < 5e-2
+    with pytest.raises(Exception):
+        lp(a, b)                                  # CPU tensors: no CPU path
 
 
 def test_tokenizer_trainer_steps_and_loss_goes_down():
@@ -200,17 +205,19 @@ def test_tokenizer_trainer_steps_and_loss_goes_down():
     assert last < first
 
 
-def test_loss_curve_parity_small_decoder():
-    """20 optimizer steps (L1 + LPIPS, AdamW, clip) on the GPU path vs the CPU oracle in autocast-emulating mode.
-    Tolerance: LPIPS is accumulated and returned in bf16 under autocast (utils/lpips.py:91-94), i.e. the loss itself
-    carries 2^-8 = 3.9e-3 relative rounding noise in the reference; we require 1e-2 per step, mean below 4e-3."""
-    import json, subprocess, sys
+def test_loss_curve_parity_real_trainer_vs_stock_arms():
+    """12 steps of the REAL TokenizerTrainer (CUDA-graph replay, arena, fused clip + AdamW + EMA; ViT-B encoder, production decoder)
+    against the strict-fp32 stock-PyTorch anchor and the cuDNN-autocast control arm (scripts/loss_parity.py, scripts/stock_arms.py).
+    Tolerance: the reference's own autocast run carries the bf16 rounding of the LPIPS tail (2^-8 = 3.9e-3 relative on that term,
+    utils/lpips.py:91-94), so the bound is 1e-2 per step and "not worse than twice the control arm's own distance to fp32"."""
+    import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "loss_parity.py"), "--steps", "20", "--batch", "2", "--small"],
-                         capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stderr[-2000:]
-    r = json.loads(out.stdout.strip().splitlines()[-1])
-    assert r["max_rel_loss_diff"] < 1e-2 and r["mean_rel_loss_diff"] < 4e-3, r
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    import loss_parity
+    r = loss_parity.run_parity(torch.device(DEV), steps=12, global_batch=2, size="base", cuda_graph=True, micro=2)
+    assert r["ours_vs_anchor_fp32"]["max"] < 1e-2, r
+    assert r["ours_vs_anchor_fp32"]["max"] <= 2.0 * r["control_vs_anchor_fp32"]["max"] + 1e-3, r
+    assert r["ours_vs_control_cudnn_autocast"]["mean"] < 4e-3, r
 
 
 @pytest.mark.parametrize("tag,tol", [("fp32_cfg5", 1e-5), ("fp32_cfg1", 1e-5), ("bf16_cfg5", 1e-2)])
