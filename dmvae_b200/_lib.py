@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvae_b200.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 1          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
+ABI_VERSION = 3          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> argtypes  (every function returns int except dmvae_last_error)
@@ -36,7 +36,7 @@ SIGNATURES = {
     "dmvae_gn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _i, _p],
     "dmvae_pack_weights": [_p, _p, _p, _i, _i, _i, _i, _p],
     "dmvae_conv_tc_supported": [_i] * 7,
-    "dmvae_conv_tc_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "dmvae_conv_tc_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "dmvae_conv_tc_set_tile_mode": [_i],
     "dmvae_conv_tc_strided_supported": [_i] * 10,
     "dmvae_conv_tc_fwd_strided": [_p, _p, _p, _p] + [_i] * 12 + [_p],
@@ -46,7 +46,10 @@ SIGNATURES = {
     "dmvae_conv_tc_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "dmvae_wgrad_unpack": [_p, _p, _i, _i, _i, _i, _p],
     "dmvae_grad_patches": [_p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p],
-    "dmvae_conv_direct_fwd": [_p, _p, _p, _p, _p] + [_i] * 12 + [_p],
+    "dmvae_conv_direct_fwd": [_p, _p, _p, _p, _p] + [_i] * 13 + [_p],
+    "dmvae_maxpool2x2_fwd": [_p, _p, _i64, _i, _i, _i, _p],
+    "dmvae_pool_tap_bwd": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
+    "dmvae_relu_mask": [_p, _p, _p, _i64, _p],
     "dmvae_conv_direct_dgrad_strided": [_p, _p, _p] + [_i] * 12 + [_p],
     "dmvae_conv_direct_wgrad": [_p, _p, _p] + [_i] * 12 + [_p],
     "dmvae_bias_grad": [_p, _p, _i64, _i, _p],
@@ -58,7 +61,9 @@ SIGNATURES = {
     "dmvae_scale_residual": [_p, _p, _p, _i64, _i, _p],
     "dmvae_layernorm_bf16": [_p, _p, _p, _p, _i64, _i, _f, _p],
     "dmvae_grad_sumsq": [_p, _p, _i64, _p],
-    "dmvae_adamw_ema_step": [_p, _p, _p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _f, _p],
+    "dmvae_adamw_ema_step": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _f, _p],
+    "dmvae_cast_bf16": [_p, _p, _i64, _p],
+    "dmvae_pack_dgrad_bf16": [_p, _p, _i, _i, _i, _p],
 }
 
 _lib: Optional[C.CDLL] = None

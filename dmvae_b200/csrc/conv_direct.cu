@@ -13,6 +13,7 @@
 
 struct ConvGeom {
     int B, H, W, Cin, OH, OW, Cout, KH, KW, stride, pt, pl;
+    int flags;          // 1 = ReLU on the output, 2 = `res` gates the output (res > 0 ? y : 0) instead of being added (see conv_tc.cu)
 };
 
 // ---- generic 64x64x32 smem-tiled implicit GEMM ---------------------------------------------------------------
@@ -98,7 +99,11 @@ __global__ void __launch_bounds__(256) conv_direct_fwd_kernel(const bf16* __rest
             const int n = n0 + tn + j;
             if (n >= g.Cout) continue;
             float v = acc[i][j] + (bias ? bias[n] : 0.f);
-            if (res) v = bf16_round(v) + __bfloat162float(res[m * g.Cout + n]);   // bf16 conv output, then bf16 add (:82)
+            if (g.flags & 1) v = fmaxf(v, 0.f);
+            if (res) {
+                const float fr = __bfloat162float(res[m * g.Cout + n]);
+                v = (g.flags & 2) ? (fr > 0.f ? v : 0.f) : bf16_round(v) + fr;    // bf16 conv output, then bf16 add (:82)
+            }
             y[m * g.Cout + n] = __float2bfloat16_rn(v);
         }
     }
@@ -190,6 +195,10 @@ __global__ void __launch_bounds__(256) conv_thin_in_fwd_kernel(const bf16* __res
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { a0[k] += x0 * wv[k]; a1[k] += x1 * wv[k]; }
                 }
+        }
+        if (g.flags & 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { a0[k] = fmaxf(a0[k], 0.f); a1[k] = fmaxf(a1[k], 0.f); }
         }
         bf16* yp = y + (((b * g.H + h) * g.W) + w0) * g.Cout + col * 8;
         st_stream16(yp, pack_bf16x8(a0));
@@ -337,9 +346,10 @@ static int check_geom(const ConvGeom& g, const char* who) {
 
 DMVAE_API int dmvae_conv_direct_fwd(const void* x, const void* w_packed, const float* bias, const void* residual,
                                     void* y, int B, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW,
-                                    int stride, int pad_top, int pad_left, void* stream) {
+                                    int stride, int pad_top, int pad_left, int flags, void* stream) {
     DMVAE_CHECK_ARG(x && w_packed && y, "conv_direct_fwd: null pointer");
-    ConvGeom g = {B, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad_top, pad_left};
+    DMVAE_CHECK_ARG((flags & ~3) == 0 && (!(flags & 2) || residual), "conv_direct_fwd: bad flags %d", flags);
+    ConvGeom g = {B, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad_top, pad_left, flags};
     int rc = check_geom(g, "conv_direct_fwd");
     if (rc) return rc;
     if (B == 0) return DMVAE_OK;
@@ -347,7 +357,7 @@ DMVAE_API int dmvae_conv_direct_fwd(const void* x, const void* w_packed, const f
     const int64_t M = (int64_t)B * OH * OW;
     const bool vec = (Cin % 8 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)w_packed & 15) == 0);
     const size_t small_smem = (size_t)KH * KW * Cout * Cin * sizeof(float);
-    if (Cout <= 4 && vec && !residual && small_smem <= 96 * 1024) {
+    if (Cout <= 4 && vec && !residual && !flags && small_smem <= 96 * 1024) {
         const unsigned grid = (unsigned)ceil_div64(M, 128);
 #define SMALL(CO)                                                                                                    \
     {                                                                                                                \

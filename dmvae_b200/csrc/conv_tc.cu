@@ -144,10 +144,16 @@ __device__ __forceinline__ void chunk_group_stats(const float (&r)[32], double* 
     }
 }
 
+// Epilogue flags (dmvae_conv_tc_fwd `flags`): EPI_RELU = y = max(conv + bias, 0) (VGG16's conv -> ReLU, utils/lpips.py:116-153);
+// EPI_MASK = the `residual` tensor is not added but gates the output, y = residual > 0 ? y : 0 -- the backward of the ReLU that
+// produced this (data-gradient) conv's input, applied where the gradient is written instead of in a separate pass.
+constexpr int EPI_RELU = 1, EPI_MASK = 2;
+
 // One 32-column chunk of one accumulator row: + bias, bf16 rounding, optional residual add, 64-byte store, optional stats.
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int n, int64_t pix, const float* __restrict__ bias,
                                                const bf16* __restrict__ res, bf16* __restrict__ out, int Cout,
-                                               double* __restrict__ st /* stats of this image or null */, int cpg, int lane) {
+                                               double* __restrict__ st /* stats of this image or null */, int cpg, int lane,
+                                               int flags = 0) {
     bf16* op = out + pix * Cout + n;
     const bf16* rp = res ? res + pix * Cout + n : nullptr;
     if (n + 32 <= Cout && (Cout & 7) == 0) {
@@ -167,11 +173,20 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int n, i
                 float f[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
+                if (flags & EPI_RELU) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                }
                 if (rp) {
                     float fr[8];
                     unpack_bf16x8(rr[qq], fr);
+                    if (flags & EPI_MASK) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];   // bf16 conv output, then bf16 add
+                        for (int e = 0; e < 8; ++e) f[e] = fr[e] > 0.f ? f[e] : 0.f;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];   // bf16 conv output, then bf16 add
+                    }
                 }
                 pk[qq] = pack_bf16x8(f);
                 if (st) {
@@ -197,7 +212,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int n, i
     } else {
         for (int e = 0; e < 32 && n + e < Cout; ++e) {
             float f = __uint_as_float(v[e]) + (bias ? __ldg(bias + n + e) : 0.f);
-            if (rp) f = bf16_round(f) + __bfloat162float(rp[e]);
+            if (flags & EPI_RELU) f = fmaxf(f, 0.f);
+            if (rp) {
+                const float fr = __bfloat162float(rp[e]);
+                f = (flags & EPI_MASK) ? (fr > 0.f ? f : 0.f) : bf16_round(f) + fr;
+            }
             op[e] = __float2bfloat16_rn(f);
         }
     }
@@ -207,7 +226,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int n, i
 // while the tile's main loop was still running / while the previous chunk was being stored).
 __device__ __forceinline__ void epilogue_chunk_pre(const uint32_t (&v)[32], int n, int64_t pix, const float* __restrict__ bias,
                                                    const uint4 (&rv)[4], bool has_res, bf16* __restrict__ out, int Cout,
-                                                   double* __restrict__ st, int cpg, int lane) {
+                                                   double* __restrict__ st, int cpg, int lane, int flags = 0) {
     bf16* op = out + pix * Cout + n;
     float r[32];
     const bool wide = (Cout & 15) == 0 && ((uintptr_t)out & 31) == 0;
@@ -220,11 +239,20 @@ __device__ __forceinline__ void epilogue_chunk_pre(const uint32_t (&v)[32], int 
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + (bias ? __ldg(bias + n + q * 8 + e) : 0.f);
+            if (flags & EPI_RELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
             if (has_res) {
                 float fr[8];
                 unpack_bf16x8(rv[q], fr);
+                if (flags & EPI_MASK) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];
+                    for (int e = 0; e < 8; ++e) f[e] = fr[e] > 0.f ? f[e] : 0.f;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = bf16_round(f[e]) + fr[e];
+                }
             }
             pk[qq] = pack_bf16x8(f);
             if (st) {
@@ -273,10 +301,43 @@ __device__ __forceinline__ void epilogue_load_residual(const bf16* __restrict__ 
 #pragma unroll
     for (int it = 0; it < 8; ++it) rv[it] = ld_stream16(res_tile + off[it] + n);
 }
+// GroupNorm statistics in the line-coalesced epilogue.  In the read-back phase a lane owns 8 consecutive channels of 8 pixel rows,
+// and for the decoder's widths those 8 channels are whole groups (C = 128: two groups of 4, C = 256: one group of 8) or half of one
+// (C = 512: 16 channels = two adjacent lanes), so the per-group {sum, sum of squares} cost 8 FADD/FFMA per 16-byte vector, two or
+// three shuffles per warp and block, and one fp64 atomic pair from 4..16 lanes -- instead of the 10 shuffles per group and
+// 32-channel chunk of the per-thread-row form (chunk_group_stats), which made fused statistics a loss for narrow groups.
+__device__ __forceinline__ bool line_stats_ok(int cpg) { return cpg == 4 || cpg == 8 || cpg == 16; }
+__device__ __forceinline__ void block64_group_stats(const float (&gs)[8], const float (&gq)[8], double* __restrict__ st, int n,
+                                                    int cpg, int lane) {
+    const int c = lane & 7;                              // this lane's channels: n + 8c .. n + 8c + 7
+    float s0 = (gs[0] + gs[1]) + (gs[2] + gs[3]), s1 = (gs[4] + gs[5]) + (gs[6] + gs[7]);
+    float q0 = (gq[0] + gq[1]) + (gq[2] + gq[3]), q1 = (gq[4] + gq[5]) + (gq[6] + gq[7]);
+    if (cpg != 4) { s0 += s1; q0 += q1; }
+    if (cpg == 16) { s0 += __shfl_xor_sync(0xffffffffu, s0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 1); }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {                  // the four lanes that hold the same channels of different rows
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+        if (cpg == 4) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+    }
+    if (lane < 8) {
+        const int ch = n + 8 * c;
+        if (cpg == 4) {
+            atomicAdd(&st[(ch >> 2) * 2], (double)s0); atomicAdd(&st[(ch >> 2) * 2 + 1], (double)q0);
+            atomicAdd(&st[((ch >> 2) + 1) * 2], (double)s1); atomicAdd(&st[((ch >> 2) + 1) * 2 + 1], (double)q1);
+        } else if (cpg == 8) {
+            atomicAdd(&st[(ch >> 3) * 2], (double)s0); atomicAdd(&st[(ch >> 3) * 2 + 1], (double)q0);
+        } else if ((c & 1) == 0) {
+            atomicAdd(&st[(ch >> 4) * 2], (double)s0); atomicAdd(&st[(ch >> 4) * 2 + 1], (double)q0);
+        }
+    }
+}
+
 __device__ __forceinline__ void epilogue_block64(uint32_t taddr, int n, const int (&off)[8], const float* __restrict__ bias,
                                                  const uint4 (&rv)[8], bool has_res, bf16* __restrict__ out_tile,
-                                                 uint4* __restrict__ patch, int lane) {
+                                                 uint4* __restrict__ patch, int lane, int flags = 0,
+                                                 double* __restrict__ st = nullptr, int cpg = 0) {
     const int c = lane & 7, rsub = lane >> 3;
+    float gs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -295,6 +356,10 @@ __device__ __forceinline__ void epilogue_block64(uint32_t taddr, int n, const in
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
             }
+            if (flags & EPI_RELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
             patch[lane * 8 + ((half * 4 + q) ^ (lane & 7))] = pack_bf16x8(f);
         }
     }
@@ -307,26 +372,39 @@ __device__ __forceinline__ void epilogue_block64(uint32_t taddr, int n, const in
             float f[8], fr[8];
             unpack_bf16x8(pk, f);
             unpack_bf16x8(rv[it], fr);
+            if (flags & EPI_MASK) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] += fr[e];               // bf16 conv output + bf16 residual, one rounding
+                for (int e = 0; e < 8; ++e) f[e] = fr[e] > 0.f ? f[e] : 0.f;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += fr[e];           // bf16 conv output + bf16 residual, one rounding
+            }
             pk = pack_bf16x8(f);
         }
         *reinterpret_cast<uint4*>(out_tile + off[it] + n) = pk;
+        if (st) {                                                     // statistics of the values as stored (bf16)
+            float fo[8];
+            unpack_bf16x8(pk, fo);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { gs[e] += fo[e]; gq[e] = fmaf(fo[e], fo[e], gq[e]); }
+        }
     }
+    if (st) block64_group_stats(gs, gq, st, n, cpg, lane);
     __syncwarp();
 }
 // all 64-channel blocks of one warp's 32 rows: the residual of block i+1 is in flight while block i is processed
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int n0, int n_end, const int (&off)[8], const float* __restrict__ bias,
                                               const bf16* __restrict__ res_tile, uint4 (&rv)[8], bf16* __restrict__ out_tile,
-                                              uint4* __restrict__ patch, int lane) {
+                                              uint4* __restrict__ patch, int lane, int flags = 0,
+                                              double* __restrict__ st = nullptr, int cpg = 0) {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 64) {
         if (n0 + c0 >= n_end) break;
         uint4 rn[8];
         const bool more = res_tile && c0 + 64 < BN && n0 + c0 + 64 < n_end;
         if (more) epilogue_load_residual(res_tile, n0 + c0 + 64, off, rn);
-        epilogue_block64(taddr + c0, n0 + c0, off, bias, rv, res_tile != nullptr, out_tile, patch, lane);
+        epilogue_block64(taddr + c0, n0 + c0, off, bias, rv, res_tile != nullptr, out_tile, patch, lane, flags, st, cpg);
         if (more) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) rv[it] = rn[it];
@@ -338,6 +416,7 @@ struct TcGeom {
     int B, H, W, Cin, Cout, KH, KW, pt, pl;      // H, W: OUTPUT image size (tiles live on the output grid)
     int stride, IH, IW;                          // conv stride and INPUT image size (IH = H, IW = W when stride == 1)
     int cpg;               // Cout / 32 (GroupNorm group width) when output statistics are requested
+    int flags;             // EPI_RELU | EPI_MASK
     int BW, BH;            // pixel tile = BH rows x BW cols of one image (BH*BW = 128)
     int tiles_w, tiles_h;  // W/BW, H/BH
     int m_tiles, n_tiles, k_chunks;
@@ -467,7 +546,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tmem_ld32(taddr + c0, v);
                 const int n = n0 + c0;
                 if (n >= g.Cout) continue;                            // warp-uniform
-                epilogue_chunk(v, n, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
+                epilogue_chunk(v, n, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane, g.flags);
             }
             tc_fence_before();
             __syncwarp();
@@ -650,7 +729,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_wait(&tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
-            if (!stats && (g.Cout & 63) == 0) {
+            if ((!stats || line_stats_ok(g.cpg)) && (g.Cout & 63) == 0) {
                 EpiGeom eg;
                 eg.tile_pix0 = ((int64_t)b * g.H + th * g.BH) * g.W + tw * g.BW;
                 eg.W = g.W; eg.bw_shift = 31 - __clz(g.BW); eg.bw_mask = g.BW - 1; eg.Cout = g.Cout;
@@ -660,7 +739,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const bf16* res_tile = res ? res + eg.tile_pix0 * g.Cout : nullptr;
                 uint4 rv[8];
                 if (res_tile) epilogue_load_residual(res_tile, n0, off, rv);
-                epilogue_rows<BN>(taddr, n0, g.Cout, off, bias, res_tile, rv, out + eg.tile_pix0 * g.Cout, patch, lane);
+                epilogue_rows<BN>(taddr, n0, g.Cout, off, bias, res_tile, rv, out + eg.tile_pix0 * g.Cout, patch, lane, g.flags,
+                                  stats ? stats + (int64_t)b * 64 : nullptr, g.cpg);
             } else {
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -668,7 +748,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     tmem_ld32(taddr + c0, v);
                     const int n = n0 + c0;
                     if (n >= g.Cout) continue;
-                    epilogue_chunk(v, n, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane);
+                    epilogue_chunk(v, n, pix, bias, res, out, g.Cout, stats ? stats + (int64_t)b * 64 : nullptr, g.cpg, lane, g.flags);
                 }
             }
             tc_fence_before();
@@ -828,7 +908,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
             const int64_t pix = ((int64_t)b * g.H + th * HALO_H + dh) * g.W + tw * HALO_W + dw;
             const int n0 = nt * BN;
-            if (!stats) {
+            if (!stats || line_stats_ok(g.cpg)) {
                 // residual rows of the first block are fetched (line-coalesced) while the main loop of this tile still runs
                 EpiGeom eg;
                 eg.tile_pix0 = ((int64_t)b * g.H + th * HALO_H) * g.W + tw * HALO_W;
@@ -842,7 +922,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 mbar_wait(&tfull[buf], (it >> 1) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * BN;
-                epilogue_rows<BN>(taddr, n0, g.Cout, off, bias, res_tile, rv, out + eg.tile_pix0 * g.Cout, patch, lane);
+                epilogue_rows<BN>(taddr, n0, g.Cout, off, bias, res_tile, rv, out + eg.tile_pix0 * g.Cout, patch, lane, g.flags,
+                                  stats ? stats + (int64_t)b * 64 : nullptr, g.cpg);
             } else {
                 // fused GroupNorm statistics: per-thread rows (the statistics are reduced per pixel row), residual one chunk ahead
                 const bf16* rp = res ? res + pix * g.Cout + n0 : nullptr;
@@ -862,7 +943,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
-                    epilogue_chunk_pre(v, n0 + c0, pix, bias, rv, rp != nullptr, out, g.Cout, stats + (int64_t)b * 64, g.cpg, lane);
+                    epilogue_chunk_pre(v, n0 + c0, pix, bias, rv, rp != nullptr, out, g.Cout, stats + (int64_t)b * 64, g.cpg, lane, g.flags);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) rv[q] = rn[q];
                 }
@@ -903,7 +984,8 @@ struct CfgT {
 
 __global__ void __launch_bounds__(CfgT::THREADS, 1)
 conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out, TcGeom g) {
+                const float* __restrict__ bias, const bf16* __restrict__ res, bf16* __restrict__ out,
+                double* __restrict__ stats /* GroupNorm(32) statistics of the output, group width 4 (Cout = 128), or null */, TcGeom g) {
     using C = CfgT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1034,7 +1116,11 @@ conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         for (int j = 0; j < 32; ++j) {
                             const int64_t idx = (pix0 + (int64_t)((n0 + j) >> 3) * g.W + ((n0 + j) & 7)) * g.Cout + cw + lane;
                             float f = __uint_as_float(v[j]) + bs;
-                            if (res) f = bf16_round(f) + __bfloat162float(res[idx]);
+                            if (g.flags & EPI_RELU) f = fmaxf(f, 0.f);
+                            if (res) {
+                                const float fr = __bfloat162float(res[idx]);
+                                f = (g.flags & EPI_MASK) ? (fr > 0.f ? f : 0.f) : bf16_round(f) + fr;
+                            }
                             out[idx] = __float2bfloat16_rn(f);
                         }
                     }
@@ -1044,13 +1130,17 @@ conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 if (lane == 0) mbar_arrive(&tempty[buf]);
                 continue;
             }
+            float ts0 = 0.f, tq0 = 0.f, ts1 = 0.f, tq1 = 0.f;      // this lane's two groups of 4 channels (fused GroupNorm statistics)
 #pragma unroll
             for (int c0 = 0; c0 < 128; c0 += 32) {
                 if (!live) break;                      // warp-uniform
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) patch[j * 32 + lane] = __float2bfloat16_rn(__uint_as_float(v[j]) + bv);
+                for (int j = 0; j < 32; ++j) {
+                    const float f = __uint_as_float(v[j]) + bv;
+                    patch[j * 32 + lane] = __float2bfloat16_rn((g.flags & EPI_RELU) ? fmaxf(f, 0.f) : f);
+                }
                 __syncwarp();
                 const int n0 = half * 128 + c0;        // 32 pixel columns = 4 image rows of 8 pixels
 #pragma unroll
@@ -1062,13 +1152,38 @@ conv_tcT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         float f[8], fr[8];
                         unpack_bf16x8(pk, f);
                         unpack_bf16x8(rv[(c0 >> 3) + q], fr);
+                        if (g.flags & EPI_MASK) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] += fr[e];               // bf16 conv output + bf16 residual, one rounding
+                            for (int e = 0; e < 8; ++e) f[e] = fr[e] > 0.f ? f[e] : 0.f;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] += fr[e];           // bf16 conv output + bf16 residual, one rounding
+                        }
                         pk = pack_bf16x8(f);
                     }
                     *reinterpret_cast<uint4*>(out + idx) = pk;
+                    if (stats) {
+                        float fo[8];
+                        unpack_bf16x8(pk, fo);
+                        ts0 += (fo[0] + fo[1]) + (fo[2] + fo[3]);
+                        tq0 += (fo[0] * fo[0] + fo[1] * fo[1]) + (fo[2] * fo[2] + fo[3] * fo[3]);
+                        ts1 += (fo[4] + fo[5]) + (fo[6] + fo[7]);
+                        tq1 += (fo[4] * fo[4] + fo[5] * fo[5]) + (fo[6] * fo[6] + fo[7] * fo[7]);
+                    }
                 }
                 __syncwarp();
+            }
+            if (stats && live) {                       // lanes with the same `grp` hold the same channels of different pixels
+#pragma unroll
+                for (int o = 4; o <= 16; o <<= 1) {
+                    ts0 += __shfl_xor_sync(0xffffffffu, ts0, o); tq0 += __shfl_xor_sync(0xffffffffu, tq0, o);
+                    ts1 += __shfl_xor_sync(0xffffffffu, ts1, o); tq1 += __shfl_xor_sync(0xffffffffu, tq1, o);
+                }
+                if (px_l == 0) {
+                    double* st = stats + (int64_t)b * 64 + ((cw + grp * 8) >> 2) * 2;
+                    atomicAdd(st, (double)ts0); atomicAdd(st + 1, (double)tq0);
+                    atomicAdd(st + 2, (double)ts1); atomicAdd(st + 3, (double)tq1);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -1558,7 +1673,7 @@ int launch_conv_tc2h(const void* x, const void* w, const float* bias, const void
     return DMVAE_OK;
 }
 
-int launch_conv_tcT(const void* x, const void* w, const float* bias, const void* res, void* y, TcGeom g, cudaStream_t st) {
+int launch_conv_tcT(const void* x, const void* w, const float* bias, const void* res, void* y, double* stats, TcGeom g, cudaStream_t st) {
     using C = CfgT;
     CUtensorMap mx, mw;
     const uint64_t xdims[4] = {(uint64_t)g.Cin, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
@@ -1577,7 +1692,7 @@ int launch_conv_tcT(const void* x, const void* w, const float* bias, const void*
     }
     const int tiles = g.m_tiles * g.n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    conv_tcT_kernel<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mx, mw, bias, (const bf16*)res, (bf16*)y, g);
+    conv_tcT_kernel<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mx, mw, bias, (const bf16*)res, (bf16*)y, stats, g);
     DMVAE_CHECK_LAUNCH("conv_tcT_kernel");
     return DMVAE_OK;
 }
@@ -1602,7 +1717,9 @@ DMVAE_API int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, in
 // stride-1 "same" convolution (3x3 pad 1 or 1x1 pad 0) on the tensor cores.
 //   y = conv(x, w_packed) + bias [; y = bf16(y) + residual]
 DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
-                                double* gn_stats, int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream) {
+                                double* gn_stats, int B, int H, int W, int Cin, int Cout, int KH, int KW, int flags, void* stream) {
+    DMVAE_CHECK_ARG((flags & ~(EPI_RELU | EPI_MASK)) == 0, "conv_tc_fwd: unknown flags %d", flags);
+    DMVAE_CHECK_ARG(!(flags & EPI_MASK) || residual, "conv_tc_fwd: the mask flag needs the mask tensor in `residual`");
     DMVAE_CHECK_ARG(x && w_packed && y, "conv_tc_fwd: null pointer");
     DMVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
                     ((uintptr_t)residual & 15) == 0, "conv_tc_fwd: buffers must be 16-byte aligned");
@@ -1612,6 +1729,7 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
     g.pt = (KH - 1) / 2; g.pl = (KW - 1) / 2;
     g.stride = 1; g.IH = H; g.IW = W;
+    g.flags = flags;
     double* stats = nullptr;
     g.cpg = 0;
     if (gn_stats) {
@@ -1636,14 +1754,15 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     if (g_force_mt == 2 && bn >= 128 && pick_pixel_tile_n(H, W, 2 * BM, &bw2, &bh2)) mt = 2;
     // transposed halo tiles for 128-channel outputs (an N = 128 instruction only half-fills the tensor pipe)
     if (g_halo && (g_force_mt == 0 || g_halo == 2) && KH == 3 && KW == 3 && ((bn == 128 && Cout % 64 == 0) || (bn == 32 && Cout < 32)) &&
-        Cin % BK == 0 && !stats && W % HALO_W == 0 && H % THALO_H == 0 && (((uintptr_t)y | (uintptr_t)residual) & 15) == 0) {
+        Cin % BK == 0 && (!stats || (Cout == 128 && g.cpg == 4)) && W % HALO_W == 0 && H % THALO_H == 0 &&
+        (((uintptr_t)y | (uintptr_t)residual) & 15) == 0) {
         TcGeom gt = g;
         gt.BW = HALO_W; gt.BH = THALO_H;
         gt.tiles_w = W / HALO_W; gt.tiles_h = H / THALO_H;
         gt.m_tiles = B * gt.tiles_w * gt.tiles_h;
         gt.n_tiles = (Cout + BM - 1) / BM;
         if (g_halo == 2 || gt.m_tiles * gt.n_tiles >= (num_sms() * 3) / 4)
-            return launch_conv_tcT(x, w_packed, bias, residual, y, gt, st);
+            return launch_conv_tcT(x, w_packed, bias, residual, y, stats, gt, st);
     }
     // halo-resident CTA pairs: 3x3 filters, 16 x 8 pixel tiles, full N tiles, at least ~3/8 of a wave of pair tiles
     if (g_halo && (g_force_mt == 0 || g_halo == 2) && KH == 3 && KW == 3 && bn >= 128 && Cout % bn == 0 && Cin % BK == 0 && W % HALO_W == 0 && H % HALO_H == 0 &&
@@ -1831,7 +1950,7 @@ DMVAE_API int dmvae_conv_tc_fwd_strided(const void* x, const void* w_packed, con
         return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_tc_fwd_strided: shape B=%d %dx%d->%dx%d Cin=%d Cout=%d s=%d not supported", B, IH, IW, OH, OW, Cin, Cout, stride);
     TcGeom g;
     g.B = B; g.H = OH; g.W = OW; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
-    g.pt = pad_top; g.pl = pad_left; g.stride = stride; g.IH = IH; g.IW = IW; g.cpg = 0;
+    g.pt = pad_top; g.pl = pad_left; g.stride = stride; g.IH = IH; g.IW = IW; g.cpg = 0; g.flags = 0;
     g.k_chunks = (Cin + BK - 1) / BK;
     pick_pixel_tile_n(OH, OW, BM, &g.BW, &g.BH);
     g.tiles_w = OW / g.BW; g.tiles_h = OH / g.BH;

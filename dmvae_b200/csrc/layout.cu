@@ -335,6 +335,38 @@ DMVAE_API int dmvae_pack_weights(const float* w, void* w_fwd, void* w_dgrad, int
     return DMVAE_OK;
 }
 
+// bf16 forward operand wf[tap][co][ci]  ->  data-gradient operand wd[taps-1-tap][ci][co] (bf16 -> bf16, one 32x32 transpose per
+// tile and tap).  Used when the forward operand is maintained by the optimizer kernel (tap-major parameter arenas, optim.py): the
+// fp32 masters are then not read again for packing.
+__global__ void __launch_bounds__(256) pack_dgrad_bf16_kernel(const bf16* __restrict__ wf, bf16* __restrict__ wd, int Cout, int Cin, int taps) {
+    __shared__ bf16 tile[32][33];
+    const int tap = blockIdx.z;
+    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const bf16* src = wf + (int64_t)tap * Cout * Cin;
+    bf16* dst = wd + (int64_t)(taps - 1 - tap) * Cin * Cout;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int co = co0 + ty + i, ci = ci0 + tx;
+        if (co < Cout && ci < Cin) tile[ty + i][tx] = src[(int64_t)co * Cin + ci];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int ci = ci0 + ty + i, co = co0 + tx;
+        if (co < Cout && ci < Cin) dst[(int64_t)ci * Cout + co] = tile[tx][ty + i];
+    }
+}
+
+DMVAE_API int dmvae_pack_dgrad_bf16(const void* w_fwd, void* w_dgrad, int Cout, int Cin, int taps, void* stream) {
+    DMVAE_CHECK_ARG(w_fwd && w_dgrad, "pack_dgrad_bf16: null pointer");
+    DMVAE_CHECK_ARG(Cout > 0 && Cin > 0 && taps > 0 && taps <= 64, "pack_dgrad_bf16: bad shape");
+    dim3 grid((unsigned)((Cout + 31) / 32), (unsigned)((Cin + 31) / 32), (unsigned)taps);
+    pack_dgrad_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)w_fwd, (bf16*)w_dgrad, Cout, Cin, taps);
+    DMVAE_CHECK_LAUNCH("pack_dgrad_bf16_kernel");
+    return DMVAE_OK;
+}
+
 // tap-major wgrad scratch [tap][Cout][Cin] -> state_dict layout dw[co][ci][tap] (accumulate=1: +=).
 // One CTA per (co, 256-wide ci chunk): taps coalesced row reads, shared-memory interleave, one contiguous write.
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restrict__ dwp, float* __restrict__ dw,

@@ -4,6 +4,8 @@
 // after the bias-corrected sqrt) and torch.nn.utils.clip_grad_norm_ (coef = min(1, max_norm / (norm + 1e-6))).
 //   pass 1: acc[0] += sum g^2                                              4 B / parameter
 //   pass 2: g *= coef ; m, v, p, ema updated                               20 B read + 16 B written / parameter
+//           (+ 2 B written: w16 = bf16(p), the conv tiles' forward operand -- for arenas that keep 3x3 conv weights tap-major
+//            ([tap][Cout][Cin], optim.py) this IS the packed bf16 weight, so no separate pack_weights pass reads the fp32 masters again)
 #include "common.cuh"
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, double* __restrict__ acc, int64_t n) {
@@ -34,7 +36,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                                        float* __restrict__ v, float* __restrict__ ema,
+                                                        float* __restrict__ v, float* __restrict__ ema, bf16* __restrict__ w16,
                                                         const double* __restrict__ sumsq, float* __restrict__ norm_out,
                                                         int64_t n, AdamArgs a) {
     float coef = 1.f;
@@ -56,9 +58,27 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, f
         *reinterpret_cast<float4*>(m + 4 * i) = M;
         *reinterpret_cast<float4*>(v + 4 * i) = V;
         if (ema) *reinterpret_cast<float4*>(ema + 4 * i) = E;
+        if (w16) {
+            uint2 pk;
+            pk.x = pack_bf16x2(P.x, P.y); pk.y = pack_bf16x2(P.z, P.w);
+            *reinterpret_cast<uint2*>(w16 + 4 * i) = pk;
+        }
     }
-    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         adam_one(p[i], g[i], m[i], v[i], ema ? ema + i : nullptr, a, coef);
+        if (w16) w16[i] = __float2bfloat16_rn(p[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+    const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 P = *reinterpret_cast<const float4*>(src + 4 * i);
+        uint2 pk;
+        pk.x = pack_bf16x2(P.x, P.y); pk.y = pack_bf16x2(P.z, P.w);
+        *reinterpret_cast<uint2*>(dst + 4 * i) = pk;
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
 static unsigned opt_grid(int64_t n) {
@@ -80,12 +100,13 @@ DMVAE_API int dmvae_grad_sumsq(const float* g, double* sumsq, int64_t n, void* s
 
 // One AdamW step on flat arenas.  sumsq (optional): device fp64 sum of squared gradients -> global-norm clip with
 // max_norm (<= 0: no clip) and norm_out[0] = ||g||.  ema (optional): ema = decay*ema + (1-decay)*p_new.  step >= 1.
-DMVAE_API int dmvae_adamw_ema_step(float* p, float* g, float* m, float* v, float* ema, const double* sumsq, float* norm_out,
+// w16 (optional): bf16 copy of the updated parameters, same element order.
+DMVAE_API int dmvae_adamw_ema_step(float* p, float* g, float* m, float* v, float* ema, void* w16, const double* sumsq, float* norm_out,
                                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                                    float max_norm, float ema_decay, void* stream) {
     DMVAE_CHECK_ARG(p && g && m && v, "adamw_ema_step: null pointer");
     DMVAE_CHECK_ARG(n >= 0 && step >= 1, "adamw_ema_step: bad size or step");
-    DMVAE_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema) & 15) == 0,
+    DMVAE_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema | (uintptr_t)w16) & 15) == 0,
                     "adamw_ema_step: arenas must be 16-byte aligned");
     if (n == 0) return DMVAE_OK;
     AdamArgs a;
@@ -93,7 +114,17 @@ DMVAE_API int dmvae_adamw_ema_step(float* p, float* g, float* m, float* v, float
     a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     a.max_norm = max_norm; a.ema_decay = ema_decay;
-    adamw_ema_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, sumsq, norm_out, n, a);
+    adamw_ema_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, (bf16*)w16, sumsq, norm_out, n, a);
     DMVAE_CHECK_LAUNCH("adamw_ema_kernel");
+    return DMVAE_OK;
+}
+
+// dst (bf16) = src (fp32), n elements: (re)build the bf16 copy of a parameter arena outside an optimizer step.
+DMVAE_API int dmvae_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    DMVAE_CHECK_ARG(src && dst, "cast_bf16: null pointer");
+    DMVAE_CHECK_ARG(n >= 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "cast_bf16: bad size or alignment");
+    if (n == 0) return DMVAE_OK;
+    cast_bf16_kernel<<<opt_grid(n), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+    DMVAE_CHECK_LAUNCH("cast_bf16_kernel");
     return DMVAE_OK;
 }

@@ -1,10 +1,10 @@
 """LPIPS with the reference's surface (utils/lpips.py:52-161) and a fused feature-distance reduction.
 
 State-dict keys are the reference's: ``scaling_layer.{shift,scale}``, ``net.slice{1..5}.{idx}.{weight,bias}``,
-``lin{0..4}.model.1.weight``.  The VGG16 convolutions stay library calls (cuDNN, channels-last bf16 under
-autocast; SURVEY.md row N3 is a later widening); everything after the taps -- channel-normalise, squared
-difference, 1x1 ``lin`` weighting, spatial mean (utils/lpips.py:86-91, ~50 ATen launches and six HBM passes in the
-reference) -- is one kernel per tap reading each feature map exactly once.
+``lin{0..4}.model.1.weight``.  The frozen VGG16 trunk runs on this library's conv tiles with ReLU / max-pool fused
+(``vgg16.forward_b200``); everything after the taps -- channel-normalise, squared difference, 1x1 ``lin``
+weighting, spatial mean (utils/lpips.py:86-91, ~50 ATen launches and six HBM passes in the reference) -- is one kernel
+per tap reading each feature map exactly once.
 """
 from __future__ import annotations
 
@@ -77,25 +77,30 @@ class vgg16(nn.Module):
         return outs
 
     def forward_b200(self, X):
-        """Frozen-weight VGG16 pass on the library's own conv tiles: channels-last bf16 activations,
-        tcgen05 implicit-GEMM convs (thin-input kernel for the 3->64 stem), same bf16/fp32 rounding points as the
-        autocast'ed cuDNN path.  ReLU / max-pool stay ATen elementwise ops.  X: (B, 3, H, W) fp32 or bf16."""
+        """Frozen-weight VGG16 pass on the library's own kernels: channels-last bf16 activations, tcgen05
+        implicit-GEMM convs with the ReLU in their epilogue (thin-input kernel for the 3->64 stem), own 2x2 max-pool; in backward
+        every ReLU gate rides in a data-gradient epilogue or in the pool backward, which also adds the LPIPS tap gradient
+        (ops.ConvReluFn / ops.PoolTapFn) -- no elementwise or ATen pooling launches.  Same bf16 / fp32 rounding points as the
+        autocast'ed cuDNN path.  X: (B, 3, H, W) fp32 or bf16; returns the five taps as NCHW-logical views."""
         packs = self.__dict__.setdefault("_packs", {})
         h = ops.to_channels_last(X)                                   # (B, H, W, 3) bf16
         outs = []
+        x_is_relu = False                                             # the image / a pooled map: no ReLU gate on the way back
         for k in range(1, 6):
-            for name, m in getattr(self, f"slice{k}").named_children():
-                if isinstance(m, nn.Conv2d):
-                    key = f"slice{k}.{name}"
-                    pack = packs.get(key)
-                    if pack is None:
-                        pack = packs[key] = ops.WeightPack()
-                    h = ops.conv2d(h, m.weight, m.bias, pack)
-                elif isinstance(m, nn.ReLU):
-                    h = torch.relu(h)
-                else:
-                    h = nn.functional.max_pool2d(h.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
-            outs.append(h.permute(0, 3, 1, 2))                        # NCHW-logical view of the channels-last buffer
+            convs = [(name, m) for name, m in getattr(self, f"slice{k}").named_children() if isinstance(m, nn.Conv2d)]
+            if k > 1:                                                 # the slice starts with the pool of the previous tap
+                tap, h = ops.pool_tap(h)
+                outs.append(tap.permute(0, 3, 1, 2))
+                x_is_relu = False
+            for i, (name, m) in enumerate(convs):
+                key = f"slice{k}.{name}"
+                pack = packs.get(key)
+                if pack is None:
+                    pack = packs[key] = ops.WeightPack()
+                last = k == 5 and i == len(convs) - 1                 # relu5_3: consumed by the LPIPS tap only, nobody gates for it
+                h = ops.conv_relu(h, m.weight, m.bias, pack, x_is_relu, dy_premasked=not last)
+                x_is_relu = True
+        outs.append(h.permute(0, 3, 1, 2))                            # NCHW-logical views of the channels-last buffers
         return outs
 
 

@@ -20,11 +20,12 @@ from . import _lib
 from ._lib import BF16, F32, call, ptr, query
 
 GN_EPS = 1e-6
-# The conv epilogue can reduce the next GroupNorm's statistics.  The cross-pixel warp reduction costs 10 shuffles per
-# group per 32-channel chunk, which only pays when groups are wide; below this group width the separate (HBM-bound)
-# gn_stats pass is cheaper (measured on B200: 16 -> channels >= 512).
+EPI_RELU, EPI_MASK = 1, 2      # conv epilogue flags (csrc/conv_tc.cu): ReLU on the output / `residual` gates the output
+# The conv epilogue reduces the next GroupNorm's statistics.  The line-coalesced epilogues of the pair / halo tiles and the transposed
+# tile do it for group widths 4 / 8 / 16 (C = 128 / 256 / 512) at a few FADDs per stored vector; the per-thread-row epilogue of the
+# remaining tiles handles any width that divides 32.  Below this group width the separate (HBM-bound) gn_stats pass is used.
 import os as _os
-FUSE_GN_STATS_MIN_CPG = int(_os.environ.get("DMVAE_FUSE_GN_STATS_MIN_CPG", "16"))
+FUSE_GN_STATS_MIN_CPG = int(_os.environ.get("DMVAE_FUSE_GN_STATS_MIN_CPG", "4"))
 
 
 def _chk_nhwc(x: torch.Tensor, name: str) -> torch.Tensor:
@@ -50,6 +51,15 @@ class WeightPack:
     def get(self, weight: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         v = weight._version
         if self.w_fwd is None or v != self.version or weight.data_ptr() != self.data_ptr or self.w_fwd.device != weight.device:
+            w16 = getattr(weight, "_dmvae_w16", None)
+            if w16 is not None and getattr(weight, "_dmvae_w16_version", None) == v and w16.device == weight.device:
+                # the optimizer kernel keeps a bf16 copy of this (tap-major) parameter: that IS w_fwd; only the transposed
+                # data-gradient operand is derived here, bf16 -> bf16 (optim.FlatAdamWEMA, csrc/optim.cu)
+                taps, cout, cin = w16.shape
+                wd = torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=w16.device)
+                call("dmvae_pack_dgrad_bf16", ptr(w16), ptr(wd), cout, cin, taps)
+                self.w_fwd, self.w_dgrad, self.version, self.data_ptr = w16, wd, v, weight.data_ptr()
+                return self.w_fwd, self.w_dgrad
             w = weight.detach()
             if w.dtype != torch.float32:
                 w = w.float()
@@ -67,9 +77,10 @@ class WeightPack:
 def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
                      kh: int, kw: int, stride: int = 1, pad_tl: Tuple[int, int] = (1, 1),
                      out_hw: Optional[Tuple[int, int]] = None, force_direct: bool = False,
-                     pad_br: Optional[Tuple[int, int]] = None, want_gn_stats: bool = False) -> torch.Tensor:
+                     pad_br: Optional[Tuple[int, int]] = None, want_gn_stats: bool = False, flags: int = 0) -> torch.Tensor:
     """y = conv(x, w_packed[tap][Cout][Cin]) + bias (+ residual).  Picks the tcgen05 tile when the shape allows.
-    pad_tl / pad_br: zero padding (top, left) / (bottom, right); pad_br defaults to pad_tl."""
+    pad_tl / pad_br: zero padding (top, left) / (bottom, right); pad_br defaults to pad_tl.
+    flags: EPI_RELU -> y = max(y, 0); EPI_MASK -> ``residual`` is not added but gates the output (y where residual > 0, else 0)."""
     B, H, W, cin = x.shape
     taps, cout, cin_w = w_packed.shape
     assert taps == kh * kw and cin_w == cin, (w_packed.shape, x.shape, kh, kw)
@@ -87,15 +98,15 @@ def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[tor
         if want_gn_stats and cout % 32 == 0 and cout // 32 >= FUSE_GN_STATS_MIN_CPG and \
                 (cout // 32 in (1, 2, 4, 8, 16) or (cout // 32) % 32 == 0):
             stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
-        call("dmvae_conv_tc_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), ptr(stats), B, H, W, cin, cout, kh, kw)
+        call("dmvae_conv_tc_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), ptr(stats), B, H, W, cin, cout, kh, kw, flags)
         if stats is not None:
             y._dmvae_gnstats = (stats, y.data_ptr(), tuple(y.shape), _ver(y))       # consumed by the next GroupNorm
-    elif (stride == 2 and residual is None and not force_direct
+    elif (stride == 2 and residual is None and not force_direct and not flags
           and query("dmvae_conv_tc_strided_supported", B, H, W, cin, OH, OW, cout, kh, kw, stride)):
         call("dmvae_conv_tc_fwd_strided", ptr(x), ptr(w_packed), ptr(bias), ptr(y), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
     else:
         call("dmvae_conv_direct_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), B, H, W, cin, OH, OW, cout,
-             kh, kw, stride, pt, pl)
+             kh, kw, stride, pt, pl, flags)
     return y
 
 
@@ -134,31 +145,51 @@ def _grad_done(p) -> None:
         a.notify(p)
 
 
+def _is_tap_major(t: torch.Tensor, cout: int, cin: int, kh: int, kw: int) -> bool:
+    """t is a (Cout, Cin, KH, KW) view of a dense [KH*KW][Cout][Cin] block (train_arena.arena_view), 16-byte aligned."""
+    return (t.dtype == torch.float32 and tuple(t.shape) == (cout, cin, kh, kw) and t.data_ptr() % 16 == 0
+            and (kh * kw == 1 and t.is_contiguous() or t.stride() == (cin, 1, kw * cout * cin, cout * cin)))
+
+
 def conv_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, stride: int = 1, pad_tl: Tuple[int, int] = (1, 1),
                    force_direct: bool = False, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
-    """dw (Cout, Cin, KH, KW) fp32 = sum_pixels dy (x) x.  With ``out`` (a contiguous fp32 tensor of that shape) the result is
-    ACCUMULATED into it and None is returned."""
+    """dw (Cout, Cin, KH, KW) fp32 = sum_pixels dy (x) x.  With ``out`` (an fp32 tensor of that shape) the result is
+    ACCUMULATED into it and None is returned; when ``out`` is a tap-major arena view the tensor-core kernels accumulate
+    straight into its storage (no scratch, no un-packing pass)."""
     B, H, W, cin = x.shape
     _, OH, OW, cout = dy.shape
     pt, pl = pad_tl
     same = stride == 1 and OH == H and OW == W and pt == (kh - 1) // 2 and pl == (kw - 1) // 2
+    direct_out = out is not None and _is_tap_major(out, cout, cin, kh, kw)
     if same and not force_direct and query("dmvae_conv_tc_wgrad_supported", B, H, W, cin, cout, kh, kw):
+        if direct_out:
+            call("dmvae_conv_tc_wgrad", ptr(x), ptr(dy), ptr(out), B, H, W, cin, cout, kh, kw)
+            return None
         scratch = torch.zeros((kh * kw, cout, cin), dtype=torch.float32, device=x.device)
         call("dmvae_conv_tc_wgrad", ptr(x), ptr(dy), ptr(scratch), B, H, W, cin, cout, kh, kw)
-        if out is not None:
+        if out is not None and out.is_contiguous():
             call("dmvae_wgrad_unpack", ptr(scratch), ptr(out), cout, cin, kh * kw, 1)
             return None
         dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
         call("dmvae_wgrad_unpack", ptr(scratch), ptr(dw), cout, cin, kh * kw, 0)
+        if out is not None:
+            out.add_(dw)
+            return None
         return dw
     if stride == 2 and not force_direct and query("dmvae_conv_tc_strided_supported", B, H, W, cin, OH, OW, cout, kh, kw, stride):
+        if direct_out:
+            call("dmvae_conv_tc_wgrad_strided", ptr(x), ptr(dy), ptr(out), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
+            return None
         scratch = torch.zeros((kh * kw, cout, cin), dtype=torch.float32, device=x.device)
         call("dmvae_conv_tc_wgrad_strided", ptr(x), ptr(dy), ptr(scratch), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
-        if out is not None:
+        if out is not None and out.is_contiguous():
             call("dmvae_wgrad_unpack", ptr(scratch), ptr(out), cout, cin, kh * kw, 1)
             return None
         dw = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
         call("dmvae_wgrad_unpack", ptr(scratch), ptr(dw), cout, cin, kh * kw, 0)
+        if out is not None:
+            out.add_(dw)
+            return None
         return dw
     dw = torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
     call("dmvae_conv_direct_wgrad", ptr(x), ptr(dy), ptr(dw), B, H, W, cin, OH, OW, cout, kh, kw, stride, pt, pl)
@@ -169,14 +200,20 @@ def conv_wgrad_raw(x: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, stride: 
 
 
 def conv_dgrad_raw(dy: torch.Tensor, w_fwd: torch.Tensor, w_dgrad: torch.Tensor, in_hw: Tuple[int, int], kh: int, kw: int,
-                   stride: int = 1, pad_tl: Tuple[int, int] = (1, 1), force_direct: bool = False) -> torch.Tensor:
+                   stride: int = 1, pad_tl: Tuple[int, int] = (1, 1), force_direct: bool = False,
+                   relu_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """relu_mask: the conv's own input when that input is a ReLU output -- the data gradient is zeroed where it is <= 0 in the
+    epilogue (the upstream ReLU's backward, fused); stride-1 "same" convs only."""
     B, OH, OW, cout = dy.shape
     H, W = in_hw
     pt, pl = pad_tl
     cin = w_fwd.shape[2]
     if stride == 1 and OH == H and OW == W:
         # "same" conv: dX = conv(dY, flipped/transposed weights) with the mirrored padding
-        return conv_forward_raw(dy, w_dgrad, None, None, kh, kw, 1, (kh - 1 - pt, kw - 1 - pl), (H, W), force_direct)
+        return conv_forward_raw(dy, w_dgrad, None, relu_mask, kh, kw, 1, (kh - 1 - pt, kw - 1 - pl), (H, W), force_direct,
+                                flags=EPI_MASK if relu_mask is not None else 0)
+    if relu_mask is not None:
+        raise _lib.DmvaeError("conv_dgrad_raw: relu_mask is only supported for stride-1 'same' convolutions")
     if (stride == 2 and kh == 3 and kw == 3 and pt == 0 and pl == 0 and H == 2 * OH and W == 2 * OW and cout % 8 == 0
             and not force_direct and query("dmvae_conv_tc_supported", B, H, W, cout, cin, 3, 3)):
         # Downsample (pad (0,1,0,1)): dx = conv3x3_same(zero-inserted dy, flipped weights) on the tensor cores
@@ -405,6 +442,83 @@ class GroupNormSiluSkipFn(torch.autograd.Function):
         dx, dgamma, dbeta = gn_bwd_raw(da, x, stats, g, b, ctx.silu, dres=dres, want_colsum=True, out_dgamma=sg, out_dbeta=sb)
         _affine_done(ctx, sg)
         return dx, dgamma, dbeta, None
+
+
+class ConvReluFn(torch.autograd.Function):
+    """relu(conv3x3(x) + b) with FROZEN weights: VGG16's conv -> ReLU pairs (utils/lpips.py:116-153, requires_grad=False at :121).
+    The ReLU forward is the conv epilogue; its backward is never a pass of its own:
+      * ``x_is_relu``: x is itself a ReLU output, so the data gradient is gated by x > 0 in the dgrad epilogue (that is the
+        backward of the ReLU that produced x);
+      * ``dy_premasked``: whoever consumes y already gates the gradient it sends back by y > 0 (a ConvReluFn with x_is_relu, or
+        PoolTapFn); only when that is not the case (the last tap) is a small mask kernel run here."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pack: WeightPack, x_is_relu: bool, dy_premasked: bool):
+        if weight.requires_grad or (bias is not None and bias.requires_grad):
+            raise _lib.DmvaeError("ConvReluFn is for frozen convolutions (LPIPS' VGG16); use conv2d for trainable ones")
+        x = _chk_nhwc(x, "conv_relu")
+        cout, cin, kh, kw = weight.shape
+        w_fwd, w_dgrad = pack.get(weight)
+        y = conv_forward_raw(x, w_fwd, None if bias is None else bias.detach(), None, kh, kw, 1, ((kh - 1) // 2, (kw - 1) // 2),
+                             flags=EPI_RELU)
+        ctx.geom = (kh, kw, x.shape[1:3])
+        ctx.save_for_backward(x if x_is_relu else None, None if dy_premasked else y, w_fwd, w_dgrad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, w_fwd, w_dgrad = ctx.saved_tensors
+        kh, kw, in_hw = ctx.geom
+        dy = _chk_nhwc(dy, "conv_relu backward")
+        if y is not None:
+            masked = torch.empty_like(dy)
+            call("dmvae_relu_mask", ptr(y), ptr(dy), ptr(masked), dy.numel())
+            dy = masked
+        dx = conv_dgrad_raw(dy, w_fwd, w_dgrad, in_hw, kh, kw, 1, ((kh - 1) // 2, (kw - 1) // 2), relu_mask=x)
+        return dx, None, None, None, None, None
+
+
+class PoolTapFn(torch.autograd.Function):
+    """y -> (y, max_pool2d(y, 2, 2)) for a ReLU output y that is both an LPIPS tap and the input of the next VGG slice
+    (utils/lpips.py:127-153).  Backward adds the tap gradient and the routed pool gradient and gates the sum by y > 0 in one
+    kernel (no ATen max-pool backward, no gradient add, no ReLU backward)."""
+
+    @staticmethod
+    def forward(ctx, y):
+        y = _chk_nhwc(y, "pool_tap")
+        B, H, W, c = y.shape
+        if H % 2 or W % 2 or c % 8:
+            raise _lib.DmvaeError(f"pool_tap: need even H, W and C % 8 == 0, got {tuple(y.shape)}")
+        p = torch.empty((B, H // 2, W // 2, c), dtype=y.dtype, device=y.device)
+        call("dmvae_maxpool2x2_fwd", ptr(y), ptr(p), B, H // 2, W // 2, c)
+        ctx.save_for_backward(y)
+        return y.view_as(y), p
+
+    @staticmethod
+    def backward(ctx, d_tap, d_pooled):
+        (y,) = ctx.saved_tensors
+        B, H, W, c = y.shape
+        if d_pooled is None:                             # only the tap was used
+            if d_tap is None:
+                return None
+            d_tap = _chk_nhwc(d_tap, "pool_tap backward")
+            out = torch.empty_like(y)
+            call("dmvae_relu_mask", ptr(y), ptr(d_tap), ptr(out), y.numel())
+            return out
+        d_pooled = _chk_nhwc(d_pooled, "pool_tap backward")
+        d_tap = None if d_tap is None else _chk_nhwc(d_tap, "pool_tap backward")
+        dy = torch.empty_like(y)
+        call("dmvae_pool_tap_bwd", ptr(y), ptr(d_pooled), ptr(d_tap), ptr(dy), B, H // 2, W // 2, c, 1)
+        return dy
+
+
+def conv_relu(x, weight, bias, pack: WeightPack, x_is_relu: bool, dy_premasked: bool = True):
+    return ConvReluFn.apply(x, weight, bias, pack, x_is_relu, dy_premasked)
+
+
+def pool_tap(y):
+    """Returns (tap, pooled)."""
+    return PoolTapFn.apply(y)
 
 
 class Upsample2xFn(torch.autograd.Function):

@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from ._lib import call, ptr
-from .train_arena import GradArena
+from .train_arena import GradArena, arena_view
 
 
 class FlatAdamWEMA:
@@ -32,23 +32,39 @@ class FlatAdamWEMA:
             raise RuntimeError("FlatAdamWEMA needs CUDA parameters (dmvae_b200 has no CPU path)")
         n = self.arena.flat.numel()
         dev = self.arena.flat.device
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
-        off = 0
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         with torch.no_grad():
-            for p in self.params:                       # move every parameter's storage into the flat buffer
-                view = self.flat_p[off:off + p.numel()].view_as(p)
+            for p, off in zip(self.params, self.arena.offsets):     # move every parameter's storage into the flat buffer
+                view = arena_view(self.flat_p, off, p)              # (3x3 conv weights: tap-major storage, strided view)
                 view.copy_(p.data)
                 p.data = view
-                off += p.numel()
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
         self.ema = self.flat_p.clone() if ema_decay is not None else None
+        # bf16 copy of the parameters, rewritten by the optimizer kernel: for conv weights (tap-major, or 1x1) the view
+        # [taps][Cout][Cin] of it IS the conv tiles' packed forward operand (ops.WeightPack picks it up through p._dmvae_w16)
+        self.w16 = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        for p, off in zip(self.params, self.arena.offsets):
+            if p.ndim == 4 and (p.shape[2] * p.shape[3] == 1 or (p.shape[2] == 3 and p.shape[3] == 3)):
+                co, ci, kh, kw = p.shape
+                p._dmvae_w16 = self.w16[off:off + p.numel()].view(kh * kw, co, ci)
+                p._dmvae_w16_version = -1
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.ema_decay = 0.0 if ema_decay is None else ema_decay
         self.t = 0
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._ema_synced_at = tuple(p._version for p in self.params)
+        self.sync_w16()
+
+    def sync_w16(self) -> None:
+        """Rebuild the bf16 copy from the fp32 parameters as they are now and mark it current (construction, after
+        ``load_state_dict``, before a CUDA-graph capture).  Until this or the next ``step()`` runs, ops.WeightPack sees a stale
+        version stamp and packs from the fp32 parameter itself."""
+        call("dmvae_cast_bf16", ptr(self.flat_p), ptr(self.w16), self.flat_p.numel())
+        for p in self.params:
+            if hasattr(p, "_dmvae_w16"):
+                p._dmvae_w16_version = p._version
 
     def sync_ema(self) -> None:
         """EMA := current weights.  The reference deep-copies the model into ``vae_ema`` after the weights are in place
@@ -67,21 +83,23 @@ class FlatAdamWEMA:
         n = self.flat_p.numel()
         self._sumsq.zero_()
         call("dmvae_grad_sumsq", ptr(self.arena.flat), ptr(self._sumsq), n)
-        call("dmvae_adamw_ema_step", ptr(self.flat_p), ptr(self.arena.flat), ptr(self.m), ptr(self.v), ptr(self.ema),
+        call("dmvae_adamw_ema_step", ptr(self.flat_p), ptr(self.arena.flat), ptr(self.m), ptr(self.v), ptr(self.ema), ptr(self.w16),
              ptr(self._sumsq), ptr(self._norm), n, float(self.lr if lr is None else lr), float(self.betas[0]),
              float(self.betas[1]), float(self.eps), float(self.wd), int(self.t), float(self.max_norm), float(self.ema_decay))
         torch.autograd.graph.increment_version(self.params)      # the kernel wrote through raw pointers
+        for p in self.params:
+            if hasattr(p, "_dmvae_w16"):
+                p._dmvae_w16_version = p._version                # ... and refreshed the bf16 operand copy with them
         return self._norm[0]
 
     # ------------------------------------------------------------------------------------------------ EMA views / checkpoints
     def ema_state(self, named_params: Dict[str, nn.Parameter]) -> Dict[str, torch.Tensor]:
         """EMA tensors keyed like ``named_parameters()`` (the trainable part of the reference's ``vae_ema`` checkpoint entry)."""
-        out, off = {}, 0
+        out = {}
         by_id = {id(p): k for k, p in named_params.items()}
-        for p in self.params:
+        for p, off in zip(self.params, self.arena.offsets):
             if id(p) in by_id and self.ema is not None:
-                out[by_id[id(p)]] = self.ema[off:off + p.numel()].view_as(p)
-            off += p.numel()
+                out[by_id[id(p)]] = arena_view(self.ema, off, p)
         return out
 
     def ema_state_dict(self, module: nn.Module) -> Dict[str, torch.Tensor]:
@@ -89,14 +107,15 @@ class FlatAdamWEMA:
         tensor replaced by its EMA value; frozen parameters (the stage-1 encoder) and buffers are the live ones, exactly what
         ``update_ema`` leaves in the reference's deep-copied model (train_tokenizer.py:140-150 only touches requires_grad
         parameters).  Loads with ``strict=True``."""
-        sd = {k: v.detach().clone() for k, v in module.state_dict().items()}
+        sd = {k: v.detach().clone(memory_format=torch.contiguous_format) for k, v in module.state_dict().items()}
         for k, v in self.ema_state(dict(module.named_parameters())).items():
-            sd[k] = v.detach().clone()
+            sd[k] = v.detach().clone(memory_format=torch.contiguous_format)
         return sd
 
     def state_dict(self) -> Dict[str, object]:
-        """The ``opt_vae`` checkpoint entry: moments, step count, hyper-parameters and the EMA arena (flat, in arena order;
-        ``numel`` / ``shapes`` guard against loading into a different parameter set)."""
+        """The ``opt_vae`` checkpoint entry: moments, step count, hyper-parameters and the EMA arena (flat, in arena order and
+        layout -- 3x3 conv weights tap-major, parameters padded to 8 elements; ``shapes`` guards against loading into a different
+        parameter set)."""
         return {"step": self.t, "exp_avg": self.m.detach().clone(), "exp_avg_sq": self.v.detach().clone(),
                 "ema": None if self.ema is None else self.ema.detach().clone(),
                 "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "max_norm": self.max_norm,

@@ -146,7 +146,8 @@ class _GraphedSection:
     that every buffer the capture allocated in the graph's private pool holds real data (an eager pass right after the capture
     would otherwise see an unchanged version counter and read packs that were only *recorded*, never written)."""
 
-    def __init__(self, fn: Callable[[], Dict[str, torch.Tensor]], params: List[nn.Parameter], warmup: int = 2):
+    def __init__(self, fn: Callable[[], Dict[str, torch.Tensor]], params: List[nn.Parameter], warmup: int = 2,
+                 optimizers: Tuple = ()):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -156,6 +157,8 @@ class _GraphedSection:
         torch.cuda.synchronize()
         if params:
             torch.autograd.graph.increment_version(params)
+        for opt in optimizers:                          # ... with the optimizer-maintained bf16 operand copies marked current, so the
+            opt.sync_w16()                              # capture records the cheap path (only the dgrad transposes are re-derived)
         self.graph = torch.cuda.CUDAGraph()
         # with a process group alive its watchdog thread polls CUDA events concurrently: only this thread's calls belong to the capture
         mode = "thread_local" if GradArena._distributed() else "global"
@@ -170,16 +173,16 @@ class _GraphedSection:
 
 
 def _capture_with_exchange(fn: Callable[[], Dict[str, torch.Tensor]], arenas: List[GradArena], params: List[nn.Parameter],
-                           warmup: int) -> Tuple[_GraphedSection, str]:
+                           warmup: int, optimizers: Tuple = ()) -> Tuple[_GraphedSection, str]:
     """Capture ``fn`` (which ends with ``arena.allreduce()``) with the chunked NCCL all-reduces INSIDE the graph: the hooks fire
     during the captured backward, each collective lands on NCCL's stream as a forked branch of the graph and overlaps the
     rest of backward on every replay.  If the process group cannot be captured, fall back to a graph without the exchange
     (hooks off; the caller issues ``arena.allreduce()`` after each replay).  Returns (section, "in-graph" | "post-replay")."""
     distributed = GradArena._distributed()
     if not distributed:
-        return _GraphedSection(fn, params, warmup), "none"
+        return _GraphedSection(fn, params, warmup, optimizers), "none"
     try:
-        return _GraphedSection(fn, params, warmup), "in-graph"
+        return _GraphedSection(fn, params, warmup, optimizers), "in-graph"
     except Exception as e:                              # noqa: BLE001
         import warnings
         warnings.warn(f"NCCL exchange could not be captured ({type(e).__name__}: {e}); capturing without it")
@@ -187,7 +190,32 @@ def _capture_with_exchange(fn: Callable[[], Dict[str, torch.Tensor]], arenas: Li
     for a in arenas:
         a.hooks_enabled = False
         a.begin_step()
-    return _GraphedSection(fn, params, warmup), "post-replay"
+    return _GraphedSection(fn, params, warmup, optimizers), "post-replay"
+
+
+class _PinnedTimes:
+    """The CPU-drawn diffusion times (transport.py:111-114: ``torch.rand`` on the CPU generator) on their way to a static device
+    buffer without a host sync: a small ring of pinned fp32 buffers, each guarded by an event so that a buffer is only redrawn
+    after the asynchronous copy that read it has completed (the host may run many replayed steps ahead of the device)."""
+
+    def __init__(self, batch: int, depth: int = 8):
+        self.bufs = [torch.empty(batch, dtype=torch.float32, pin_memory=True) for _ in range(depth)]
+        self.events: List[Optional[torch.cuda.Event]] = [None] * depth
+        self.i = 0
+
+    def send(self, dst: torch.Tensor, cpu_generator: Optional[torch.Generator], t0: float = 0.0, t1: float = 1.0) -> None:
+        k = self.i % len(self.bufs)
+        self.i += 1
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+        buf = self.bufs[k]
+        torch.rand(buf.shape, generator=cpu_generator, out=buf)
+        if t0 != 0.0 or t1 != 1.0:
+            buf.mul_(t1 - t0).add_(t0)
+        dst.copy_(buf, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
 
 
 class TokenizerTrainer:
@@ -233,7 +261,7 @@ class TokenizerTrainer:
 
             def body():                             # hooks off (fallback capture) = the exchange is issued after each replay
                 return self._forward_backward(self._gx, exchange=self.arena.hooks_enabled)
-            self._section, self.exchange_mode = _capture_with_exchange(body, [self.arena], self.params, warmup)
+            self._section, self.exchange_mode = _capture_with_exchange(body, [self.arena], self.params, warmup, (self.fused,))
             self._exchange_outside = self.exchange_mode == "post-replay"
             return True
         except Exception as e:                      # noqa: BLE001
@@ -343,13 +371,18 @@ class DmdTrainer:
             with torch.no_grad():
                 lat0 = self._encode_only(self._gx)
             self._glat = lat0.clone()
-            self._gt_dmd = self._draw_t(lat0).clone()
-            self._gt_sit = self._gt_dmd.clone()
+            B = lat0.shape[0]
+            # raw U(0,1) draws in fp32; cast to the latents' dtype and time-shifted INSIDE the graphs (the reference does both on the device)
+            self._gt_dmd = torch.rand(B, device=lat0.device, dtype=torch.float32)
+            self._gt_sit = torch.rand(B, device=lat0.device, dtype=torch.float32)
+            self._pin_dmd, self._pin_sit = _PinnedTimes(B), _PinnedTimes(B)
+            shift = self.cfg.time_dist_shift
             for a in (self.arena_vae, self.arena_sit):
                 a.hooks_enabled = True
 
             def turn():
-                log, lat = self._vae_turn(self._gx, self._gy, self._gt_dmd, exchange=self.arena_vae.hooks_enabled)
+                log, lat = self._vae_turn(self._gx, self._gy, shift_t(self._gt_dmd.to(self._glat.dtype), shift),
+                                          exchange=self.arena_vae.hooks_enabled)
                 self._glat.copy_(lat)
                 return log
 
@@ -358,10 +391,11 @@ class DmdTrainer:
                 return {}
 
             def sit():
-                return self._sit_step(self._glat, self._gy, self._gt_sit, exchange=self.arena_sit.hooks_enabled)
-            s_turn, m1 = _capture_with_exchange(turn, [self.arena_vae], self.arena_vae.params, warmup)
+                return self._sit_step(self._glat, self._gy, shift_t(self._gt_sit.to(self._glat.dtype), shift),
+                                      exchange=self.arena_sit.hooks_enabled)
+            s_turn, m1 = _capture_with_exchange(turn, [self.arena_vae], self.arena_vae.params, warmup, (self.opt_vae,))
             s_enc = _GraphedSection(enc, [], warmup)
-            s_sit, m2 = _capture_with_exchange(sit, [self.arena_sit], self.arena_sit.params, warmup)
+            s_sit, m2 = _capture_with_exchange(sit, [self.arena_sit], self.arena_sit.params, warmup, (self.opt_sit,))
             self._sections = {"turn": s_turn, "enc": s_enc, "sit": s_sit}
             self._post = {"vae": m1 == "post-replay", "sit": m2 == "post-replay"}
             self.exchange_mode = m1 if m1 == m2 else f"{m1}/{m2}"
@@ -388,14 +422,14 @@ class DmdTrainer:
             self._gx.copy_(images, non_blocking=True)
             self._gy.copy_(labels, non_blocking=True)
             if vae_turn:
-                self._gt_dmd.copy_(self._draw_t(self._gt_dmd), non_blocking=True)
+                self._pin_dmd.send(self._gt_dmd, self.cpu_generator)
                 log = self._sections["turn"].replay()
                 if self._post["vae"]:
                     self.arena_vae.allreduce()
                 log["vae_norm"] = self.opt_vae.step()
             else:
                 self._sections["enc"].replay()
-            self._gt_sit.copy_(self._draw_t(self._gt_sit), non_blocking=True)
+            self._pin_sit.send(self._gt_sit, self.cpu_generator)
             log.update(self._sections["sit"].replay())
             if self._post["sit"]:
                 self.arena_sit.allreduce()

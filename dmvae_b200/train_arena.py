@@ -9,6 +9,26 @@ import torch.distributed as tdist
 from torch import nn
 
 
+ALIGN = 8          # elements: every parameter starts on a 32-byte (fp32) / 16-byte (bf16 copy) boundary (vector red.add, TMA)
+
+
+def tap_major(p: torch.Tensor) -> bool:
+    """3x3 conv weights are kept TAP-MAJOR in the arenas -- physical order [kh*kw][Cout][Cin], the layout of the tcgen05 weight
+    gradient and of the packed bf16 forward operand -- and exposed to PyTorch as a strided (Cout, Cin, 3, 3) view.  So the weight
+    gradient is accumulated by the kernel straight into ``p.grad``'s storage (no un-packing pass) and the optimizer's bf16 copy
+    of the updated weights is the conv tiles' operand as it stands (no packing pass).  1x1 conv weights are tap-major as they are."""
+    return p.ndim == 4 and p.shape[2] == 3 and p.shape[3] == 3
+
+
+def arena_view(flat: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
+    """The view of ``flat[off : off + p.numel()]`` that has p's shape (strided for tap-major parameters)."""
+    seg = flat[off:off + p.numel()]
+    if tap_major(p):
+        co, ci, kh, kw = p.shape
+        return seg.view(kh * kw, co, ci).permute(1, 2, 0).unflatten(2, (kh, kw))
+    return seg.view(p.shape)
+
+
 class GradArena:
     """All trainable gradients as views of one flat fp32 buffer, exchanged with one NCCL all-reduce per chunk over
     NVLink/NVSwitch instead of DDP's 25 MB buckets.  With ``overlap=True`` a chunk's all-reduce is issued from an
@@ -26,18 +46,22 @@ class GradArena:
 
     def __init__(self, params: Iterable[nn.Parameter], chunks: int = 4, overlap: bool = True):
         self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        self.offsets: List[int] = []
+        n = 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)      # padding elements stay zero (and inert in the optimizer)
         self.chunks = max(1, min(chunks, len(self.params) or 1))
         # chunk boundaries on parameter boundaries, roughly equal in bytes
         target = (n + self.chunks - 1) // self.chunks
         self.bounds: List[Tuple[int, int]] = []          # [start, end) element ranges
         self.chunk_of: Dict[int, int] = {}
-        start, off = 0, 0
+        start = 0
         for i, p in enumerate(self.params):
             self.chunk_of[id(p)] = len(self.bounds)
-            off += p.numel()
+            off = self.offsets[i + 1] if i + 1 < len(self.params) else n
             if off - start >= target or i == len(self.params) - 1:
                 self.bounds.append((start, off))
                 start = off
@@ -58,12 +82,18 @@ class GradArena:
         return tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
 
     def _attach(self):
-        off = 0
-        for p in self.params:      # (re-)attach in case an optimizer dropped the views (set_to_none)
+        for p, off in zip(self.params, self.offsets):      # (re-)attach in case an optimizer dropped the views (set_to_none)
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
-                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                p.grad = arena_view(self.flat, off, p)
             self._slots[id(p)] = p.grad
-            off += p.numel()
+
+    def flatten(self, tensors) -> torch.Tensor:
+        """Per-parameter tensors (in ``self.params`` order, parameter shapes) laid out like the arena: padded to ALIGN elements,
+        3x3 conv weights tap-major.  For comparisons against ``self.flat`` in tests and consistency checks."""
+        out = torch.zeros_like(self.flat)
+        for p, off, t in zip(self.params, self.offsets, tensors):
+            arena_view(out, off, p).copy_(t)
+        return out
 
     def slot_of(self, p):
         """The arena view that is ``p.grad`` (None for tensors this arena does not own)."""

@@ -32,6 +32,10 @@ extern "C" {
 #define DMVAE_F32 0
 #define DMVAE_BF16 1
 
+/* Bumped whenever a prototype below changes; the ctypes binding (dmvae_b200/_lib.py) refuses a library whose
+ * dmvae_abi_version() differs from the table it was written against. */
+#define DMVAE_ABI_VERSION 3
+
 const char* dmvae_last_error(void);
 int dmvae_abi_version(void);
 /* 0 if the current CUDA device is sm_100 (B200); the host layer refuses to run otherwise. */
@@ -109,6 +113,8 @@ int dmvae_gn_bwd(const void* da, const void* x, const double* stats, const float
  *   w_dgrad[taps-1-tap][Cin][Cout]     data-gradient layout (either may be NULL). */
 int dmvae_pack_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KH, int KW,
                        void* stream);
+/* w_dgrad from an existing bf16 w_fwd (the optimizer kernel maintains w_fwd for tap-major parameter arenas, see N2). */
+int dmvae_pack_dgrad_bf16(const void* w_fwd, void* w_dgrad, int Cout, int Cin, int taps, void* stream);
 
 /* 1 if the shape runs on the tcgen05 tile (stride 1, 3x3 pad 1 or 1x1, C%8==0, pixel tile divides H,W). */
 int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW);
@@ -117,9 +123,14 @@ int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int 
  * (and utils/lpips.py:116-153, the frozen VGG16) and -- fed dY and w_dgrad -- cuDNN's backward-data.
  * y = conv(x) + bias ; if residual: y = bf16(y) + residual.
  * gn_stats (optional, fp64 [B][32][2], caller-zeroed): the epilogue also accumulates {sum y, sum y^2} per (image,
- * GroupNorm group) of the stored bf16 values, i.e. the output of dmvae_gn_stats for the next GroupNorm(32). */
+ * GroupNorm group) of the stored bf16 values, i.e. the output of dmvae_gn_stats for the next GroupNorm(32).
+ * flags: DMVAE_CONV_RELU  y = max(conv(x) + bias, 0) -- the nn.ReLU after every VGG16 conv (utils/lpips.py:116-153);
+ *        DMVAE_CONV_MASK  `residual` is not added: it gates the output, y = residual > 0 ? y : 0 -- ATen's ReLU backward
+ *                         (threshold_backward) for the ReLU whose output this data-gradient conv's input was. */
+#define DMVAE_CONV_RELU 1
+#define DMVAE_CONV_MASK 2
 int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
-                      double* gn_stats, int B, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
+                      double* gn_stats, int B, int H, int W, int Cin, int Cout, int KH, int KW, int flags, void* stream);
 
 /* Stride-2 3x3 convolution (flux_ae.Downsample, :85-95: pad (0,1,0,1) => pad_top = pad_left = 0) on the tcgen05 tile:
  * the A operand is sampled with TMA element strides, the right/bottom padding is the TMA out-of-bounds fill.
@@ -163,7 +174,7 @@ int dmvae_grad_patches(const void* dy, void* patches, int64_t B, int H, int W, i
  * stride-2 Downsample :89-95) and the on-device cross-check of the tensor-core path. */
 int dmvae_conv_direct_fwd(const void* x, const void* w_packed, const float* bias, const void* residual, void* y,
                           int B, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride,
-                          int pad_top, int pad_left, void* stream);
+                          int pad_top, int pad_left, int flags /* DMVAE_CONV_* */, void* stream);
 int dmvae_conv_direct_dgrad_strided(const void* dy, const void* w_packed, void* dx, int B, int H, int W, int Cin,
                                     int OH, int OW, int Cout, int KH, int KW, int stride, int pad_top,
                                     int pad_left, void* stream);
@@ -183,6 +194,18 @@ int dmvae_nhwc_to_nchw(const void* src, void* dst, int64_t B, int C, int64_t HW,
 /* out = a + b (bf16, fp32 add, one rounding): gradient fan-in of the residual branches (:52, :82). */
 int dmvae_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------ N3: VGG16 glue of LPIPS ------------------ */
+/* nn.MaxPool2d(2, 2) between the VGG16 slices (utils/lpips.py:127-153, torchvision vgg16.features[4,9,16,23]) on channels-last
+ * bf16, C % 8 == 0: y [B][2*OH][2*OW][C] -> pooled [B][OH][OW][C]. */
+int dmvae_maxpool2x2_fwd(const void* y, void* pooled, int64_t B, int OH, int OW, int C, void* stream);
+/* Backward of a slice boundary  y -> (LPIPS tap = y, pooled = maxpool2x2(y)), y = relu(.):  one kernel instead of ATen's
+ * max_pool2d backward + the autograd gradient add + ReLU's threshold_backward:
+ *   dy = (route(d_pooled to the window's first maximum) + d_tap) * [y > 0]   (d_tap may be NULL; relu = 0 skips the gate). */
+int dmvae_pool_tap_bwd(const void* y, const void* d_pooled, const void* d_tap, void* dy, int64_t B, int OH, int OW, int C,
+                       int relu, void* stream);
+/* out = y > 0 ? dy : 0 over n bf16 elements (n % 8 == 0): ReLU backward where no conv / pool epilogue can carry it (relu5_3). */
+int dmvae_relu_mask(const void* y, const void* dy, void* out, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------ A6: frozen-encoder glue ------------------ */
 /* The timm ViT of models/vae.py:34-53 under autocast + no_grad (train_tokenizer.py:295-297 freezes it): each block computes
  * x = x + ls(attn(norm1(x))); x = x + ls(mlp(norm2(x))) with an fp32 residual stream and bf16 Linear outputs.
@@ -195,11 +218,15 @@ int dmvae_layernorm_bf16(const float* x, const float* weight, const float* bias,
 
 /* ------------------------------------------------------------------ N2: fused optimizer step ---------------- */
 /* Replaces clip_grad_norm_ + AdamW.step + update_ema (train_tokenizer.py:140-150,415-417,437; train_dmd.py:540-544) on
- * flat fp32 arenas: sumsq[0] += sum g^2 ; then g *= min(1, max_norm/(||g||+1e-6)), AdamW (torch semantics), EMA. */
+ * flat fp32 arenas: sumsq[0] += sum g^2 ; then g *= min(1, max_norm/(||g||+1e-6)), AdamW (torch semantics), EMA.
+ * w16 (optional): bf16 copy of the updated parameters in the same element order -- with 3x3 conv weights kept tap-major in the
+ * arenas this is the conv tiles' packed forward operand, i.e. the weight re-pack after optimizer.step() rides in
+ * this pass.  dmvae_cast_bf16 rebuilds it outside a step (construction, load_state_dict). */
 int dmvae_grad_sumsq(const float* g, double* sumsq, int64_t n, void* stream);
-int dmvae_adamw_ema_step(float* p, float* g, float* m, float* v, float* ema, const double* sumsq, float* norm_out,
+int dmvae_adamw_ema_step(float* p, float* g, float* m, float* v, float* ema, void* w16, const double* sumsq, float* norm_out,
                          int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                          float max_norm, float ema_decay, void* stream);
+int dmvae_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

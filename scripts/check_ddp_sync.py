@@ -14,7 +14,7 @@ import torch.distributed as dist  # noqa: E402
 
 
 def spread(tr):
-    flat_p = torch.cat([p.detach().reshape(-1) for p in tr.params])
+    flat_p = tr.fused.flat_p
     lo, hi = flat_p.clone(), flat_p.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)

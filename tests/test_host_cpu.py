@@ -23,7 +23,8 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared - {"dmvae_last_error"} == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert lib.dmvae_abi_version() == 1
+    ver = int(re.search(r"#define\s+DMVAE_ABI_VERSION\s+(\d+)", hdr).group(1))
+    assert lib.dmvae_abi_version() == ver == _lib.ABI_VERSION, "header, library and ctypes table must agree on the ABI version"
 
 
 def test_product_path_fails_loudly_without_cuda():
@@ -99,7 +100,7 @@ arena.allreduce()
 sharded = arena.flat.clone()
 # the same 8 images on one rank, without touching .grad (no hooks, no exchange)
 ref = torch.autograd.grad(net(x_all).square().mean(), list(net.parameters()))
-ref = torch.cat([g.reshape(-1) for g in ref])
+ref = arena.flatten(ref)                      # arena layout: every parameter padded to 8 elements
 assert torch.allclose(sharded, ref, rtol=1e-5, atol=1e-7), (sharded - ref).abs().max()
 assert all(p.grad.data_ptr() >= arena.flat.data_ptr() for p in net.parameters())
 # a second step reuses the arena: zero(), backward, allreduce

@@ -468,6 +468,67 @@ def test_conv_production_shapes_at_bench_batch(cin, cout, hw, res):
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
 
 
+@pytest.mark.parametrize("B,cin,cout,H,W,mode", [
+    (2, 256, 256, 32, 16, 8),      # halo-resident CTA pair (line-coalesced epilogue)
+    (2, 128, 128, 32, 16, 8),      # transposed tile
+    (2, 64, 64, 32, 16, 8),        # transposed tile, half of the channel lanes live (VGG conv1_2)
+    (1, 128, 256, 16, 16, 1),      # single-CTA per-tap tile (per-thread-row epilogue)
+    (1, 64, 128, 6, 10, 0),        # ragged image: CUDA-core kernel
+])
+def test_conv_relu_epilogue_and_relu_gated_dgrad(B, cin, cout, H, W, mode):
+    """N3: y = relu(conv(x) + b) in the conv epilogue (DMVAE_CONV_RELU) and dx = dgrad(dy) * [x > 0] in the data-gradient epilogue
+    (DMVAE_CONV_MASK: the backward of the ReLU that produced x), on every tile family, vs torch fp32 on the bf16-rounded operands."""
+    from dmvae_b200 import _lib
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(B * 1000 + cin + cout)
+    x = O.r16(torch.relu(torch.randn(B, cin, H, W, generator=g)))            # a ReLU output: about half zeros
+    w = O.r16(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+    b = torch.randn(cout, generator=g) * 0.1
+    dy = O.r16(torch.randn(B, cout, H, W, generator=g))
+    xr = x.clone().requires_grad_(True)
+    y_ref = O.r16(torch.relu(F.conv2d(xr, w, b, padding=1)))
+    F.conv2d(xr, w, None, padding=1).backward(dy)
+    dx_ref = O.r16(xr.grad) * (x > 0)
+    wf, wd = ops.WeightPack().get(w.to(DEV))
+    _lib.query("dmvae_conv_tc_set_tile_mode", mode)
+    try:
+        y = ops.conv_forward_raw(nhwc(x), wf, b.to(DEV), None, 3, 3, flags=ops.EPI_RELU)
+        dx = ops.conv_dgrad_raw(nhwc(dy), wf, wd, (H, W), 3, 3, relu_mask=nhwc(x))
+    finally:
+        _lib.query("dmvae_conv_tc_set_tile_mode", 0)
+        _lib.query("dmvae_conv_tc_set_tile_mode", 7)
+    torch.cuda.synchronize()
+    assert (nchw(y) >= 0).all()
+    assert rel_err(nchw(y), y_ref) < 4e-3
+    assert rel_err(nchw(dx), dx_ref) < 4e-3
+    assert (nchw(dx)[x == 0] == 0).all(), "gradient must be exactly zero where the ReLU output was zero"
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 16, 24), (1, 512, 4, 4), (3, 8, 2, 2)])
+def test_maxpool_and_fused_pool_tap_backward(B, C, H, W):
+    """dmvae_maxpool2x2_fwd / dmvae_pool_tap_bwd vs ATen max_pool2d (+ its backward, + the tap-gradient add, + ReLU's
+    threshold_backward) on a ReLU output with exact ties (zeros) in most windows.  Bit-exact: selection and one bf16 add."""
+    ops, _ = _ops()
+    g = torch.Generator(device=DEV).manual_seed(C + H)
+    y = torch.relu(torch.randn(B, H, W, C, generator=g, device=DEV)).bfloat16()
+    y[:, ::2, ::2, : C // 2] = y[:, 1::2, 1::2, : C // 2]                  # non-zero ties inside a window: first maximum wins
+    d_tap = torch.randn(B, H, W, C, generator=g, device=DEV).bfloat16()
+    d_pool = torch.randn(B, H // 2, W // 2, C, generator=g, device=DEV).bfloat16()
+    yl = y.clone().requires_grad_(True)
+    tap, pooled = ops.pool_tap(yl)
+    yr = y.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    pr = F.max_pool2d(yr, 2, 2)
+    assert torch.equal(pooled.permute(0, 3, 1, 2), pr)
+    (tap.float() * d_tap.float()).sum().backward(retain_graph=True)        # tap only: relu gate on the tap gradient
+    assert torch.equal(yl.grad, torch.where(y > 0, d_tap, torch.zeros_like(d_tap)))
+    yl.grad = None
+    torch.autograd.backward([tap, pooled], [d_tap, d_pool])
+    pr.backward(d_pool.permute(0, 3, 1, 2))
+    ref = (yr.grad.permute(0, 2, 3, 1).float() + d_tap.float()).bfloat16()
+    ref = torch.where(y > 0, ref, torch.zeros_like(ref))
+    assert torch.equal(yl.grad, ref)
+
+
 def test_vit_glue_scale_residual_bit_exact():
     """x += float(y) * gamma must equal the reference's two ATen passes (x + y * gamma with type promotion) bit for bit."""
     from dmvae_b200 import _lib

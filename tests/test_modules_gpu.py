@@ -208,16 +208,18 @@ def test_tokenizer_trainer_steps_and_loss_goes_down():
 def test_loss_curve_parity_real_trainer_vs_stock_arms():
     """12 steps of the REAL TokenizerTrainer (CUDA-graph replay, arena, fused clip + AdamW + EMA; ViT-B encoder, production decoder)
     against the strict-fp32 stock-PyTorch anchor and the cuDNN-autocast control arm (scripts/loss_parity.py, scripts/stock_arms.py).
-    Tolerance: the reference's own autocast run carries the bf16 rounding of the LPIPS tail (2^-8 = 3.9e-3 relative on that term,
-    utils/lpips.py:91-94), so the bound is 1e-2 per step and "not worse than twice the control arm's own distance to fp32"."""
+    Same weights per step: the reference's own autocast run carries the bf16 rounding of the LPIPS tail (2^-8 relative on that term,
+    utils/lpips.py:91-94) -- bound 5e-3 per step and "not worse than 1.5x the control arm's own distance to fp32".  Free running:
+    AdamW's first steps amplify bf16 gradient noise into trajectory differences; bound = twice the control arm's drift."""
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "scripts"))
     import loss_parity
     r = loss_parity.run_parity(torch.device(DEV), steps=12, global_batch=2, size="base", cuda_graph=True, micro=2)
-    assert r["ours_vs_anchor_fp32"]["max"] < 1e-2, r
-    assert r["ours_vs_anchor_fp32"]["max"] <= 2.0 * r["control_vs_anchor_fp32"]["max"] + 1e-3, r
-    assert r["ours_vs_control_cudnn_autocast"]["mean"] < 4e-3, r
+    sw, fr = r["same_weights_per_step"], r["free_running_trajectories"]
+    assert sw["ours_vs_anchor_fp32"]["max"] < 5e-3, r
+    assert sw["ours_vs_anchor_fp32"]["max"] <= 1.5 * sw["control_vs_anchor_fp32"]["max"] + 1e-3, r
+    assert fr["ours_vs_anchor_fp32"]["max"] <= 2.0 * fr["control_vs_anchor_fp32"]["max"] + 2e-3, r
 
 
 @pytest.mark.parametrize("tag,tol", [("fp32_cfg5", 1e-5), ("fp32_cfg1", 1e-5), ("bf16_cfg5", 1e-2)])
@@ -366,6 +368,64 @@ def test_fused_clip_adamw_ema_matches_torch():
     assert set(net_a.state_dict().keys()) == set(net_b.state_dict().keys())
 
 
+def test_optimizer_maintained_weight_packs_and_tap_major_arena():
+    """N2 weight re-pack inside the optimizer kernel: 3x3 conv weights live tap-major in the flat arenas (strided (Cout,Cin,3,3)
+    views), the AdamW kernel writes a bf16 copy of the updated weights that IS the conv tiles' forward operand, the dgrad operand
+    is a bf16 transpose of it -- all bit-identical to packing from the fp32 state_dict tensor; an out-of-band weight change
+    falls back to the plain pack; the checkpoint surface (state_dict values, EMA dict, optimizer state round trip) is unchanged."""
+    from dmvae_b200 import ops
+    from dmvae_b200.optim import FlatAdamWEMA
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(64, 128, 3, padding=1), torch.nn.Conv2d(128, 32, 1), torch.nn.GroupNorm(32, 32)).to(DEV)
+    w3_before = net[0].weight.detach().clone()
+    opt = FlatAdamWEMA(net.parameters(), lr=1e-2, weight_decay=0.01, ema_decay=0.9)
+    w3, w1 = net[0].weight, net[1].weight
+    assert torch.equal(w3.detach(), w3_before) and not w3.is_contiguous() and w3.shape == (128, 64, 3, 3)
+    assert all(off % 8 == 0 for off in opt.arena.offsets)
+
+    def plain(w):
+        return ops.WeightPack().get(w.detach().clone(memory_format=torch.contiguous_format))
+
+    packs = {id(w3): ops.WeightPack(), id(w1): ops.WeightPack()}
+    for w in (w3, w1):
+        wf, wd = packs[id(w)].get(w)
+        rf, rd = plain(w)
+        assert wf.data_ptr() == w._dmvae_w16.data_ptr() and torch.equal(wf, rf) and torch.equal(wd, rd)
+    for it in range(3):
+        opt.arena.zero()
+        for p in opt.params:
+            p.grad.copy_(torch.randn(p.shape, device=DEV))                 # strided copy into the tap-major slot
+        ref = [p.detach().clone() for p in opt.params]
+        gref = [p.grad.detach().clone() for p in opt.params]
+        opt.step()
+        for w in (w3, w1):
+            wf, wd = packs[id(w)].get(w)
+            rf, rd = plain(w)
+            assert wf.data_ptr() == w._dmvae_w16.data_ptr() and torch.equal(wf, rf) and torch.equal(wd, rd), it
+        if it == 0:                                                       # one AdamW step from zero moments: p - lr*wd*p - lr*sign(g)
+            for p, r, gq in zip(opt.params, ref, gref):
+                assert rel(p.detach(), r * (1 - 1e-2 * 0.01) - 1e-2 * torch.sign(gq)) < 1e-4
+    with torch.no_grad():
+        w3.mul_(2.0)                                                      # out-of-band change: version stamp is stale now
+    wf, wd = packs[id(w3)].get(w3)
+    rf, rd = plain(w3)
+    assert wf.data_ptr() != w3._dmvae_w16.data_ptr() and torch.equal(wf, rf) and torch.equal(wd, rd)
+    opt.sync_w16()
+    wf, _ = packs[id(w3)].get(w3)
+    assert wf.data_ptr() == w3._dmvae_w16.data_ptr() and torch.equal(wf, rf)
+    # checkpoint surface
+    sd = net.state_dict()
+    assert sd["0.weight"].shape == (128, 64, 3, 3)
+    ema_sd = opt.ema_state_dict(net)
+    assert set(ema_sd) == set(sd) and all(v.is_contiguous() for v in ema_sd.values())
+    net2 = copy.deepcopy(net)
+    net2.load_state_dict(ema_sd, strict=True)
+    opt_sd = opt.state_dict()
+    opt2 = FlatAdamWEMA(copy.deepcopy(net).parameters(), lr=1.0)
+    opt2.load_state_dict(opt_sd)
+    assert opt2.t == opt.t and torch.equal(opt2.m, opt.m) and torch.equal(opt2.v, opt.v) and opt2.lr == opt.lr
+
+
 def test_dmd_stage_iteration_with_lightningdit():
     """BASELINE configs[2]: a train_dmd.py iteration with LightningDiT-Mini/1 teacher and student (restated in dmvae_b200.dit,
     pinned to the reference by tests/test_dit_cpu.py): VAE turn with the fused DMD loss, then the student flow-matching step."""
@@ -454,10 +514,13 @@ def test_direct_param_grads_match_autograd_accumulation():
     ref2, got2 = run(False, 2), run(True, 2)
     assert rel(got2, ref2) < max(5 * noise, 5e-3) and rel(got2, 2 * ref) < max(5 * noise, 5e-3)
     # every parameter's .grad is still its arena slot
-    off = 0
-    for p in arena.params:
-        assert p.grad.data_ptr() == arena.flat.data_ptr() + 4 * off
-        off += p.numel()
+    for p, off in zip(arena.params, arena.offsets):
+        assert p.grad.data_ptr() == arena.flat.data_ptr() + 4 * off and off % 8 == 0
+    # 3x3 conv weights are tap-major in the arena: the strided .grad view must agree with a contiguous copy element for element
+    w = dec.mid.block_1.conv1.weight
+    assert w.grad.stride() != w.grad.contiguous().stride()
+    flat_slot = arena.flat[arena.offsets[[id(q) for q in arena.params].index(id(w))]:][:w.numel()].view(9, w.shape[0], w.shape[1])
+    assert torch.equal(flat_slot.permute(1, 2, 0).reshape(w.shape), w.grad.contiguous())
 
 
 def test_tokenizer_trainer_cuda_graph_matches_eager():
