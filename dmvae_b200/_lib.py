@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvae_b200.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 3          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
+ABI_VERSION = 4          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> argtypes  (every function returns int except dmvae_last_error)
@@ -41,6 +41,12 @@ SIGNATURES = {
     "dmvae_conv_tc_strided_supported": [_i] * 10,
     "dmvae_conv_tc_fwd_strided": [_p, _p, _p, _p] + [_i] * 12 + [_p],
     "dmvae_conv_tc_wgrad_strided": [_p, _p, _p] + [_i] * 12 + [_p],
+    "dmvae_conv_up2x_supported": [_i] * 5,
+    "dmvae_subpixel_pack": [_p, _i64, _i64, _i64, _p, _p, _i, _i, _p],
+    "dmvae_conv_up2x_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "dmvae_conv_up2x_dgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "dmvae_conv_up2x_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "dmvae_subpixel_fold_wgrad": [_p, _p, _i64, _i64, _i64, _i, _i, _p],
     "dmvae_zero_insert2x": [_p, _p, _i64, _i, _i, _i, _p],
     "dmvae_conv_tc_wgrad_supported": [_i] * 7,
     "dmvae_conv_tc_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],

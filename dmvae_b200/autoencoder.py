@@ -137,6 +137,13 @@ class Upsample(_PackMixin, nn.Module):
         self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
 
     def _forward_cl(self, x: Tensor) -> Tensor:
+        if ops.upsample_conv_supported(x, self.conv.weight):
+            # sub-pixel form: four 2x2 phase convs on the low-res tensor, the upsampled tensor is never materialised
+            packs = self.__dict__.setdefault("_packs", {})
+            pack = packs.get("conv.subpixel")
+            if pack is None:
+                pack = packs["conv.subpixel"] = ops.SubpixelPack()
+            return ops.upsample_conv(x, self.conv.weight, self.conv.bias, pack, True)
         return _conv(self, "conv", self.conv, ops.upsample2x(x), gn_next=True)
 
     def forward(self, x: Tensor):

@@ -286,14 +286,15 @@ __device__ __forceinline__ void epilogue_chunk_pre(const uint32_t (&v)[32], int 
 struct EpiGeom {
     int64_t tile_pix0;     // pixel index of tile row 0
     int W, bw_shift, bw_mask, Cout;
-};
+    int pix_step;          // output pixels between horizontally / vertically adjacent tile pixels (1; 2 for the sub-pixel upsampling conv,
+};                         // whose tile is one phase of the 2x finer output grid -- W is then the OUTPUT image width)
 // row offsets (elements, relative to tile_pix0 * Cout) of the 8 pixel rows this lane touches in the read-back phase
 __device__ __forceinline__ void epilogue_row_offsets(int row0, const EpiGeom& eg, int lane, int (&off)[8]) {
     const int rsub = lane >> 3;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int rr = row0 + it * 4 + rsub;
-        off[it] = ((rr >> eg.bw_shift) * eg.W + (rr & eg.bw_mask)) * eg.Cout + (lane & 7) * 8;
+        off[it] = ((rr >> eg.bw_shift) * eg.W + (rr & eg.bw_mask)) * eg.pix_step * eg.Cout + (lane & 7) * 8;
     }
 }
 // the residual values of one 32-row x 64-channel block, line-coalesced (8 lanes = one pixel's 128 bytes)
@@ -417,6 +418,11 @@ struct TcGeom {
     int stride, IH, IW;                          // conv stride and INPUT image size (IH = H, IW = W when stride == 1)
     int cpg;               // Cout / 32 (GroupNorm group width) when output statistics are requested
     int flags;             // EPI_RELU | EPI_MASK
+    int up;                // halo pair kernel only.  1 = sub-pixel form of nearest-2x + 3x3 (flux_ae.Upsample), forward: KH = KW = 2, the
+                           // tile list runs over the 4 output phases (py, px), phase p reads taps 4p..4p+3 of a 16-tap pack and its
+                           // halo starts at (-1 + py, -1 + px); outputs land on every other pixel of the 2H x 2W image.
+                           // 2 = its data gradient: all 4 phases are accumulated into one tile of the H x W input gradient, the A
+                           // operand being the phase's pixels of the 2H x 2W output gradient (TMA element stride 2, start (-py, -px)).
     int BW, BH;            // pixel tile = BH rows x BW cols of one image (BH*BW = 128)
     int tiles_w, tiles_h;  // W/BW, H/BH
     int m_tiles, n_tiles, k_chunks;
@@ -732,7 +738,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if ((!stats || line_stats_ok(g.cpg)) && (g.Cout & 63) == 0) {
                 EpiGeom eg;
                 eg.tile_pix0 = ((int64_t)b * g.H + th * g.BH) * g.W + tw * g.BW;
-                eg.W = g.W; eg.bw_shift = 31 - __clz(g.BW); eg.bw_mask = g.BW - 1; eg.Cout = g.Cout;
+                eg.W = g.W; eg.bw_shift = 31 - __clz(g.BW); eg.bw_mask = g.BW - 1; eg.Cout = g.Cout; eg.pix_step = 1;
                 uint4* patch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 256) + (warp - 2) * 256;
                 int off[8];
                 epilogue_row_offsets(lg * 32, eg, lane, off);
@@ -820,7 +826,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const int pair_tiles = (g.m_tiles >> 1) * g.n_tiles;
+    const int pair_tiles = (g.m_tiles >> 1) * g.n_tiles * (g.up == 1 ? 4 : 1);
+    const int phases_in = g.up == 2 ? 4 : 1;                       // output phases accumulated inside one tile (sub-pixel data gradient)
     const int taps = g.KH * g.KW;
     const int HP = HALO_W + g.KW - 1;                              // halo pitch in pixels
     const uint32_t halo_bytes = (uint32_t)((HALO_H + g.KH - 1) * HP * 128);
@@ -845,19 +852,26 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
-                const int mt = 2 * (pt / g.n_tiles) + (int)rank, nt = pt % g.n_tiles;
+                const int q = g.up == 1 ? (pt >> 2) : pt;
+                const int mt = 2 * (q / g.n_tiles) + (int)rank, nt = q % g.n_tiles;
                 const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
-                const int w0 = tw * HALO_W - g.pl, h0 = th * HALO_H - g.pt, n0 = nt * BN + (int)rank * (BN / 2);
-                for (int kc = 0; kc < g.k_chunks; ++kc) {
-                    mbar_wait(&aempty[sa], pa ^ 1);
-                    if (leader) mbar_expect_tx(&afull[sa], 2 * halo_bytes);
-                    tma_load_4d_2sm(smem + sa * C::A_SLOT3, &map_a, mapa_u32(smem_u32(&afull[sa]), 0), kc * BK, w0, h0, b);
-                    if (++sa == C::SA) { sa = 0; pa ^= 1; }
-                    for (int tap = 0; tap < taps; ++tap) {
-                        mbar_wait(&bempty[sb], pb ^ 1);
-                        if (leader) mbar_expect_tx(&bfull[sb], 2 * C::B_BYTES);
-                        tma_load_3d_2sm(smem_b + sb * C::B_BYTES, &map_b, mapa_u32(smem_u32(&bfull[sb]), 0), kc * BK, n0, tap);
-                        if (++sb == C::SB) { sb = 0; pb ^= 1; }
+                const int n0 = nt * BN + (int)rank * (BN / 2);
+                for (int pi = 0; pi < phases_in; ++pi) {
+                    const int ph = g.up == 1 ? (pt & 3) : pi, py = ph >> 1, px = ph & 1;
+                    int w0 = tw * HALO_W - g.pl, h0 = th * HALO_H - g.pt, tap0 = 0;
+                    if (g.up == 1) { w0 = tw * HALO_W - 1 + px; h0 = th * HALO_H - 1 + py; tap0 = ph * 4; }
+                    if (g.up == 2) { w0 = 2 * tw * HALO_W - px; h0 = 2 * th * HALO_H - py; tap0 = ph * 4; }    // element-stride-2 map
+                    for (int kc = 0; kc < g.k_chunks; ++kc) {
+                        mbar_wait(&aempty[sa], pa ^ 1);
+                        if (leader) mbar_expect_tx(&afull[sa], 2 * halo_bytes);
+                        tma_load_4d_2sm(smem + sa * C::A_SLOT3, &map_a, mapa_u32(smem_u32(&afull[sa]), 0), kc * BK, w0, h0, b);
+                        if (++sa == C::SA) { sa = 0; pa ^= 1; }
+                        for (int tap = 0; tap < taps; ++tap) {
+                            mbar_wait(&bempty[sb], pb ^ 1);
+                            if (leader) mbar_expect_tx(&bfull[sb], 2 * C::B_BYTES);
+                            tma_load_3d_2sm(smem_b + sb * C::B_BYTES, &map_b, mapa_u32(smem_u32(&bfull[sb]), 0), kc * BK, n0, tap0 + tap);
+                            if (++sb == C::SB) { sb = 0; pb ^= 1; }
+                        }
                     }
                 }
             }
@@ -874,7 +888,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
-                for (int kc = 0; kc < g.k_chunks; ++kc) {
+                for (int pk = 0; pk < phases_in * g.k_chunks; ++pk) {          // (phase, channel chunk): one halo each
                     mbar_wait(&afull[sa], pa);
                     const uint32_t a_base = smem_u32(smem + sa * C::A_SLOT3);
                     int kh = 0, kw = 0;
@@ -885,7 +899,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem_b + sb * C::B_BYTES));
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; ++kk)
-                            umma_bf16_2sm(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kc | tap | kk) != 0);
+                            umma_bf16_2sm(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (pk | tap | kk) != 0);
                         umma_commit_2sm(&bempty[sb]);
                         if (++sb == C::SB) { sb = 0; pb ^= 1; }
                         if (++kw == g.KW) { kw = 0; ++kh; }
@@ -904,15 +918,21 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int it = 0;
         for (int pt = cluster_id; pt < pair_tiles; pt += num_clusters, ++it) {
             const int buf = it & 1;
-            const int mt = 2 * (pt / g.n_tiles) + (int)rank, nt = pt % g.n_tiles;
+            const int q = g.up == 1 ? (pt >> 2) : pt;
+            const int mt = 2 * (q / g.n_tiles) + (int)rank, nt = q % g.n_tiles;
             const int tw = mt % g.tiles_w, th = (mt / g.tiles_w) % g.tiles_h, b = mt / (g.tiles_w * g.tiles_h);
             const int64_t pix = ((int64_t)b * g.H + th * HALO_H + dh) * g.W + tw * HALO_W + dw;
             const int n0 = nt * BN;
-            if (!stats || line_stats_ok(g.cpg)) {
+            if (!stats || line_stats_ok(g.cpg) || g.up == 1) {
                 // residual rows of the first block are fetched (line-coalesced) while the main loop of this tile still runs
                 EpiGeom eg;
                 eg.tile_pix0 = ((int64_t)b * g.H + th * HALO_H) * g.W + tw * HALO_W;
-                eg.W = g.W; eg.bw_shift = 3; eg.bw_mask = HALO_W - 1; eg.Cout = g.Cout;
+                eg.W = g.W; eg.bw_shift = 3; eg.bw_mask = HALO_W - 1; eg.Cout = g.Cout; eg.pix_step = 1;
+                if (g.up == 1) {                 // this tile is phase (py, px) of the 2H x 2W output image
+                    const int py = (pt & 3) >> 1, px = pt & 1;
+                    eg.W = 2 * g.W; eg.pix_step = 2;
+                    eg.tile_pix0 = ((int64_t)b * 2 * g.H + 2 * th * HALO_H + py) * (2 * g.W) + 2 * tw * HALO_W + px;
+                }
                 uint4* patch = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512) + (warp - 2) * 256;
                 int off[8];
                 epilogue_row_offsets(lg * 32, eg, lane, off);
@@ -1231,6 +1251,8 @@ struct WgGeom {
     int BW, BH, tiles_w, tiles_h;
     int pix_tiles;          // B * tiles_h * tiles_w
     int co_tiles, ci_tiles, tap_groups, splits, tiles_per_split;
+    int up;                 // CTA-pair kernel only: 1 = sub-pixel Upsample (see dmvae_conv_up2x_fwd): 16 "taps" t = 4*phase + 2a + b; H, W are
+                            // the LOW-RES size; dy is the phase's pixels of the 2H x 2W gradient (element-stride-2 map), x the low-res input
 };
 
 // One CTA owns an (MT*128 co) x (TPC taps x BN ci) block of the tap-major gradient and walks a contiguous range of
@@ -1418,6 +1440,12 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
     const int ci_t = id % g.ci_tiles; id /= g.ci_tiles;
     const int tap = id;
     const int kh = tap / g.KW, kw = tap % g.KW;
+    // offsets of the dy box and the x box relative to the pixel tile's origin (w0, h0); the dy origin is scaled by dys
+    int dys = 1, dyw = 0, dyh = 0, xw = kw - g.pl, xh = kh - g.pt;
+    if (g.up) {
+        const int py = tap >> 3, px = (tap >> 2) & 1, a = (tap >> 1) & 1, bb = tap & 1;
+        dys = 2; dyw = px; dyh = py; xw = bb - 1 + px; xh = a - 1 + py;
+    }
     const int co0 = co_t * (2 * MT * BM) + (int)rank * (MT * BM);
     const int ci0 = ci_t * 256;
     const int t_begin = blockIdx.y * g.tiles_per_split;
@@ -1450,11 +1478,12 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
                 if (leader) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
                 const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
 #pragma unroll
-                for (int j = 0; j < 2 * MT; ++j) tma_load_4d_2sm(sa + j * WG_BOX_BYTES, &map_dy, lbar, co0 + j * 64, w0, h0, b);
+                for (int j = 0; j < 2 * MT; ++j)
+                    tma_load_4d_2sm(sa + j * WG_BOX_BYTES, &map_dy, lbar, co0 + j * 64, w0 * dys + dyw, h0 * dys + dyh, b);
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
                     tma_load_4d_2sm(sb + j * WG_BOX_BYTES, &map_x, lbar, ci0 + (int)rank * 128 + j * 64,
-                                    w0 * g.stride + kw - g.pl, h0 * g.stride + kh - g.pt, b);
+                                    w0 * g.stride + xw, h0 * g.stride + xh, b);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -1585,6 +1614,7 @@ int pick_pixel_tile_n(int H, int W, int pixels, int* BW, int* BH) {
 }
 int pick_pixel_tile(int H, int W, int* BW, int* BH) { return pick_pixel_tile_n(H, W, BM, BW, BH); }
 
+int pick_pixel_tile64(int H, int W, int* BW, int* BH);
 int g_num_sms = 0;
 int num_sms() {
     if (!g_num_sms) {
@@ -1673,6 +1703,35 @@ int launch_conv_tc2h(const void* x, const void* w, const float* bias, const void
     return DMVAE_OK;
 }
 
+// Sub-pixel modes of the halo pair kernel (TcGeom::up).  `a`: the low-res input x (up = 1) or the 2H x 2W output gradient
+// (up = 2); `w16`: the 16-tap pack [phase*4 + tap][N][K]; g.H, g.W: the LOW-RES grid the tiles live on; g.Cin = K, g.Cout = N.
+template <int BN>
+int launch_conv_tc2h_up(const void* a, const void* w16, const float* bias, void* y, double* stats, TcGeom g, cudaStream_t st) {
+    using C = CfgH<BN>;
+    CUtensorMap ma, mb;
+    const int s = g.up == 2 ? 2 : 1;
+    const uint64_t adims[4] = {(uint64_t)g.Cin, (uint64_t)(s * g.W), (uint64_t)(s * g.H), (uint64_t)g.B};
+    const uint32_t abox[4] = {BK, (uint32_t)(HALO_W + 1), (uint32_t)(HALO_H + 1), 1};
+    const uint32_t astr[4] = {1, (uint32_t)s, (uint32_t)s, 1};
+    int rc = get_tensor_map(a, 4, adims, abox, &ma, astr);
+    if (rc) return rc;
+    const uint64_t bdims[3] = {(uint64_t)g.Cin, (uint64_t)g.Cout, 16};
+    const uint32_t bbox[3] = {BK, BN / 2, 1};
+    rc = get_tensor_map(w16, 3, bdims, bbox, &mb);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2h_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return dmvae_set_error(DMVAE_ECUDA, "conv_tc2h: smem attribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int pair_tiles = (g.m_tiles / 2) * g.n_tiles * (g.up == 1 ? 4 : 1);
+    const int clusters = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
+    conv_tc2h_kernel<BN><<<2 * clusters, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, nullptr, (bf16*)y, stats, g);
+    DMVAE_CHECK_LAUNCH("conv_tc2h_kernel (sub-pixel)");
+    return DMVAE_OK;
+}
+
 int launch_conv_tcT(const void* x, const void* w, const float* bias, const void* res, void* y, double* stats, TcGeom g, cudaStream_t st) {
     using C = CfgT;
     CUtensorMap mx, mw;
@@ -1729,7 +1788,7 @@ DMVAE_API int dmvae_conv_tc_fwd(const void* x, const void* w_packed, const float
     g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
     g.pt = (KH - 1) / 2; g.pl = (KW - 1) / 2;
     g.stride = 1; g.IH = H; g.IW = W;
-    g.flags = flags;
+    g.flags = flags; g.up = 0;
     double* stats = nullptr;
     g.cpg = 0;
     if (gn_stats) {
@@ -1803,7 +1862,8 @@ int pick_pixel_tile64(int H, int W, int* BW, int* BH) {
     while (bw * 2 <= WG_PIX && W % (bw * 2) == 0) bw *= 2;
     const int bh = WG_PIX / bw;
     if (bw < 8 || H % bh != 0) return 0;
-    *BW = bw; *BH = bh;
+    if (BW) *BW = bw;
+    if (BH) *BH = bh;
     return 1;
 }
 
@@ -1845,8 +1905,10 @@ int launch_wgrad_tc2(const void* x, const void* dy, float* dwp, WgGeom g, cudaSt
     using C = Wg2Cfg<MT>;
     CUtensorMap mdy, mx;
     const uint32_t box[4] = {64, (uint32_t)g.BW, (uint32_t)g.BH, 1};
-    const uint64_t ddims[4] = {(uint64_t)g.Cout, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
-    int rc = get_tensor_map(dy, 4, ddims, box, &mdy);
+    const int dys = g.up ? 2 : 1;
+    const uint64_t ddims[4] = {(uint64_t)g.Cout, (uint64_t)(dys * g.W), (uint64_t)(dys * g.H), (uint64_t)g.B};
+    const uint32_t dstr[4] = {1, (uint32_t)dys, (uint32_t)dys, 1};
+    int rc = get_tensor_map(dy, 4, ddims, box, &mdy, dstr);
     if (rc) return rc;
     const uint64_t xdims[4] = {(uint64_t)g.Cin, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
     const uint32_t xstr[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
@@ -1860,7 +1922,7 @@ int launch_wgrad_tc2(const void* x, const void* dy, float* dwp, WgGeom g, cudaSt
     }
     g.co_tiles = g.Cout / (2 * MT * BM);
     g.ci_tiles = g.Cin / 256;
-    g.tap_groups = g.KH * g.KW;
+    g.tap_groups = g.up ? 16 : g.KH * g.KW;
     const int base = g.co_tiles * g.ci_tiles * g.tap_groups;           // clusters before the pixel split
     int splits = (num_sms() / 2) / base;
     if (splits > g.pix_tiles) splits = g.pix_tiles;
@@ -1899,7 +1961,7 @@ DMVAE_API int dmvae_conv_tc_wgrad(const void* x, const void* dy, float* dw_tap_m
     WgGeom g;
     g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
     g.pt = (KH - 1) / 2; g.pl = (KW - 1) / 2;
-    g.stride = 1; g.IH = H; g.IW = W;
+    g.stride = 1; g.IH = H; g.IW = W; g.up = 0;
     pick_pixel_tile64(H, W, &g.BW, &g.BH);
     g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
     g.pix_tiles = B * g.tiles_w * g.tiles_h;
@@ -1930,6 +1992,78 @@ DMVAE_API int dmvae_conv_tc_set_tile_mode(int mode) {
     return DMVAE_OK;
 }
 
+// ---------------------------------------------------------------- sub-pixel Upsample (flux_ae.Upsample, :98-107)
+// F.interpolate(x, 2, "nearest") followed by a 3x3 / pad 1 conv equals, for each of the four output phases (py, px),
+// a 2x2 conv on the LOW-RES input with the 3x3 taps that fall on the same input pixel summed:
+//     y[2i+py, 2j+px] = sum_{a,b in {0,1}} Wp[py][px][a][b] . x[i + a - 1 + py, j + b - 1 + px]
+//     Wp[py][.][a][.] = sum_{kh in S(py,a)} W[kh][.],   S(0,0) = {0}, S(0,1) = {1,2}, S(1,0) = {0,1}, S(1,1) = {2}   (same for kw)
+// i.e. 16 instead of 36 tap-GEMMs per low-res pixel (2.25x fewer FLOPs), no 4x larger intermediate, no upsample kernels.
+// All three passes run on the halo-resident CTA-pair tile (forward, data gradient) / the CTA-pair weight-gradient tile.
+namespace {
+int up2x_geom(TcGeom* g, int B, int H, int W, int K, int N, int up) {
+    g->B = B; g->H = H; g->W = W; g->Cin = K; g->Cout = N; g->KH = 2; g->KW = 2; g->pt = 0; g->pl = 0;
+    g->stride = 1; g->IH = H; g->IW = W; g->cpg = 0; g->flags = 0; g->up = up;
+    g->BW = HALO_W; g->BH = HALO_H; g->tiles_w = W / HALO_W; g->tiles_h = H / HALO_H;
+    g->m_tiles = B * g->tiles_w * g->tiles_h;
+    g->k_chunks = K / BK;
+    g->n_tiles = N / 256;
+    return DMVAE_OK;
+}
+}  // namespace
+
+// 1 if nearest-2x + 3x3 with these sizes runs in sub-pixel form on the tensor cores (H, W: the LOW-RES input size)
+DMVAE_API int dmvae_conv_up2x_supported(int B, int H, int W, int Cin, int Cout) {
+    if (B <= 0 || Cin % 256 != 0 || Cout % 256 != 0 || W % HALO_W != 0 || H % HALO_H != 0) return 0;
+    return ((B * (W / HALO_W) * (H / HALO_H)) % 2) == 0 && pick_pixel_tile64(H, W, nullptr, nullptr);
+}
+
+// y[B][2H][2W][Cout] = conv3x3(nearest2x(x[B][H][W][Cin])) + bias with the 16-tap sub-pixel pack wp_fwd[16][Cout][Cin]
+// (dmvae_subpixel_pack).  gn_stats as in dmvae_conv_tc_fwd (group widths 4 / 8 / 16).
+DMVAE_API int dmvae_conv_up2x_fwd(const void* x, const void* wp_fwd, const float* bias, void* y, double* gn_stats, int B, int H,
+                                  int W, int Cin, int Cout, void* stream) {
+    DMVAE_CHECK_ARG(x && wp_fwd && y, "conv_up2x_fwd: null pointer");
+    DMVAE_CHECK_ARG((((uintptr_t)x | (uintptr_t)wp_fwd | (uintptr_t)y) & 31) == 0, "conv_up2x_fwd: buffers must be 32-byte aligned");
+    if (!dmvae_conv_up2x_supported(B, H, W, Cin, Cout))
+        return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_up2x_fwd: shape B=%d H=%d W=%d Cin=%d Cout=%d not supported", B, H, W, Cin, Cout);
+    TcGeom g;
+    up2x_geom(&g, B, H, W, Cin, Cout, 1);
+    if (gn_stats) {
+        g.cpg = Cout / 32;
+        if (!(g.cpg == 4 || g.cpg == 8 || g.cpg == 16))
+            return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_up2x_fwd: fused GroupNorm statistics unsupported for Cout=%d", Cout);
+    }
+    return launch_conv_tc2h_up<256>(x, wp_fwd, bias, y, gn_stats, g, (cudaStream_t)stream);
+}
+
+// dx[B][H][W][Cin] = data gradient of the above, from dy[B][2H][2W][Cout] and wp_dgrad[16][Cin][Cout] (dmvae_subpixel_pack).
+DMVAE_API int dmvae_conv_up2x_dgrad(const void* dy, const void* wp_dgrad, void* dx, int B, int H, int W, int Cin, int Cout,
+                                    void* stream) {
+    DMVAE_CHECK_ARG(dy && wp_dgrad && dx, "conv_up2x_dgrad: null pointer");
+    DMVAE_CHECK_ARG((((uintptr_t)dy | (uintptr_t)wp_dgrad | (uintptr_t)dx) & 31) == 0, "conv_up2x_dgrad: buffers must be 32-byte aligned");
+    if (!dmvae_conv_up2x_supported(B, H, W, Cin, Cout))
+        return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_up2x_dgrad: shape B=%d H=%d W=%d Cin=%d Cout=%d not supported", B, H, W, Cin, Cout);
+    TcGeom g;
+    up2x_geom(&g, B, H, W, /*K=*/Cout, /*N=*/Cin, 2);
+    return launch_conv_tc2h_up<256>(dy, wp_dgrad, nullptr, dx, nullptr, g, (cudaStream_t)stream);
+}
+
+// dwp[16][Cout][Cin] (fp32, caller-zeroed or accumulated) += the 16 phase-tap weight gradients of the sub-pixel form:
+//   dwp[4*(2py+px) + 2a + b][co][ci] = sum_{i,j} dy[2i+py][2j+px][co] * x[i + a - 1 + py][j + b - 1 + px][ci]
+// dmvae_subpixel_fold_wgrad turns them into the 3x3 weight gradient.
+DMVAE_API int dmvae_conv_up2x_wgrad(const void* x, const void* dy, float* dwp, int B, int H, int W, int Cin, int Cout, void* stream) {
+    DMVAE_CHECK_ARG(x && dy && dwp, "conv_up2x_wgrad: null pointer");
+    DMVAE_CHECK_ARG((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dwp) & 15) == 0, "conv_up2x_wgrad: buffers must be 16-byte aligned");
+    if (!dmvae_conv_up2x_supported(B, H, W, Cin, Cout))
+        return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_up2x_wgrad: shape B=%d H=%d W=%d Cin=%d Cout=%d not supported", B, H, W, Cin, Cout);
+    WgGeom g;
+    g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = 2; g.KW = 2; g.pt = 0; g.pl = 0;
+    g.stride = 1; g.IH = H; g.IW = W; g.up = 1;
+    pick_pixel_tile64(H, W, &g.BW, &g.BH);
+    g.tiles_w = W / g.BW; g.tiles_h = H / g.BH;
+    g.pix_tiles = B * g.tiles_w * g.tiles_h;
+    return Cout % 512 == 0 ? launch_wgrad_tc2<2>(x, dy, dwp, g, (cudaStream_t)stream) : launch_wgrad_tc2<1>(x, dy, dwp, g, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------- strided convolution (flux_ae.Downsample, :85-95)
 // Stride-2 3x3 with arbitrary top/left padding: the output grid is tiled as usual and the A operand is fetched with TMA
 // element strides of 2 over the input image (right/bottom zero padding = TMA out-of-bounds fill).
@@ -1950,7 +2084,7 @@ DMVAE_API int dmvae_conv_tc_fwd_strided(const void* x, const void* w_packed, con
         return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_tc_fwd_strided: shape B=%d %dx%d->%dx%d Cin=%d Cout=%d s=%d not supported", B, IH, IW, OH, OW, Cin, Cout, stride);
     TcGeom g;
     g.B = B; g.H = OH; g.W = OW; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
-    g.pt = pad_top; g.pl = pad_left; g.stride = stride; g.IH = IH; g.IW = IW; g.cpg = 0; g.flags = 0;
+    g.pt = pad_top; g.pl = pad_left; g.stride = stride; g.IH = IH; g.IW = IW; g.cpg = 0; g.flags = 0; g.up = 0;
     g.k_chunks = (Cin + BK - 1) / BK;
     pick_pixel_tile_n(OH, OW, BM, &g.BW, &g.BH);
     g.tiles_w = OW / g.BW; g.tiles_h = OH / g.BH;
@@ -1977,7 +2111,7 @@ DMVAE_API int dmvae_conv_tc_wgrad_strided(const void* x, const void* dy, float* 
         return dmvae_set_error(DMVAE_EUNSUPPORTED, "conv_tc_wgrad_strided: shape B=%d %dx%d->%dx%d Cin=%d Cout=%d s=%d not supported", B, IH, IW, OH, OW, Cin, Cout, stride);
     WgGeom g;
     g.B = B; g.H = OH; g.W = OW; g.Cin = Cin; g.Cout = Cout; g.KH = KH; g.KW = KW;
-    g.pt = pad_top; g.pl = pad_left; g.stride = stride; g.IH = IH; g.IW = IW;
+    g.pt = pad_top; g.pl = pad_left; g.stride = stride; g.IH = IH; g.IW = IW; g.up = 0;
     g.BW = bw; g.BH = bh;
     g.tiles_w = OW / bw; g.tiles_h = OH / bh;
     g.pix_tiles = B * g.tiles_w * g.tiles_h;

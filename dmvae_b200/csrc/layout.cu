@@ -391,6 +391,94 @@ DMVAE_API int dmvae_wgrad_unpack(const float* dw_tap_major, float* dw, int Cout,
     return DMVAE_OK;
 }
 
+// ---- sub-pixel form of nearest-2x + 3x3 (flux_ae.Upsample, :98-107; see dmvae_conv_up2x_fwd in conv_tc.cu) -------------------------
+// Output phase p in {0,1} along one axis reads input offsets {-1, 0} (p = 0) or {0, +1} (p = 1); slot a in {0,1} of that 2-tap filter
+// collects the 3x3 taps k in S(p, a):  S(0,0) = {0}, S(0,1) = {1,2}, S(1,0) = {0,1}, S(1,1) = {2}.
+__host__ __device__ __forceinline__ bool subpixel_in_S(int p, int a, int k) {
+    return p == 0 ? (a == 0 ? k == 0 : k >= 1) : (a == 0 ? k <= 1 : k == 2);
+}
+
+// w3 (fp32, element strides s_co / s_ci / s_tap: state_dict or tap-major storage) ->
+//   wp_fwd  [4*(2py+px) + 2a + b][co][ci]  bf16 = sum of the 3x3 taps (kh in S(py,a), kw in S(px,b)), summed in fp32, rounded once
+//   wp_dgrad[4*(2py+px) + (3 - (2a+b))][ci][co]  bf16: the same values transposed, the 2x2 filter flipped (data-gradient operand)
+__global__ void __launch_bounds__(256) subpixel_pack_kernel(const float* __restrict__ w3, int64_t s_co, int64_t s_ci, int64_t s_tap,
+                                                            bf16* __restrict__ wf, bf16* __restrict__ wd, int Cout, int Cin) {
+    __shared__ float tile[32][33];
+    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 (ci) x 8 (co)
+    float w[4][9];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty + 8 * i, ci = ci0 + tx;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[i][k] = (co < Cout && ci < Cin) ? w3[co * s_co + ci * s_ci + k * s_tap] : 0.f;
+    }
+    for (int t = 0; t < 16; ++t) {
+        const int py = t >> 3, px = (t >> 2) & 1, a = (t >> 1) & 1, b = t & 1;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float v = 0.f;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+                    if (subpixel_in_S(py, a, kh) && subpixel_in_S(px, b, kw)) v += w[i][kh * 3 + kw];
+            const int co = co0 + ty + 8 * i, ci = ci0 + tx;
+            if (co < Cout && ci < Cin) wf[((int64_t)t * Cout + co) * Cin + ci] = __float2bfloat16_rn(v);
+            tile[ty + 8 * i][tx] = v;
+        }
+        __syncthreads();
+        const int td = (t & ~3) | (3 - (t & 3));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ci = ci0 + ty + 8 * i, co = co0 + tx;
+            if (co < Cout && ci < Cin) wd[((int64_t)td * Cin + ci) * Cout + co] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+        }
+    }
+}
+
+DMVAE_API int dmvae_subpixel_pack(const float* w3, int64_t stride_co, int64_t stride_ci, int64_t stride_tap, void* wp_fwd, void* wp_dgrad,
+                                  int Cout, int Cin, void* stream) {
+    DMVAE_CHECK_ARG(w3 && wp_fwd && wp_dgrad, "subpixel_pack: null pointer");
+    DMVAE_CHECK_ARG(Cout > 0 && Cin > 0, "subpixel_pack: bad shape");
+    dim3 grid((unsigned)((Cout + 31) / 32), (unsigned)((Cin + 31) / 32));
+    subpixel_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w3, stride_co, stride_ci, stride_tap, (bf16*)wp_fwd, (bf16*)wp_dgrad, Cout, Cin);
+    DMVAE_CHECK_LAUNCH("subpixel_pack_kernel");
+    return DMVAE_OK;
+}
+
+// dw3[co][ci][kh][kw] (element strides as above) += sum over the phase-taps that contain (kh, kw) of dwp[16][Cout][Cin]
+__global__ void __launch_bounds__(256) subpixel_fold_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw3, int64_t s_co,
+                                                                  int64_t s_ci, int64_t s_tap, int Cout, int Cin) {
+    const int64_t n = (int64_t)Cout * Cin;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin), co = (int)(i / Cin);
+        float v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = dwp[(int64_t)t * n + i];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                float acc = 0.f;
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                    if (subpixel_in_S(t >> 3, (t >> 1) & 1, kh) && subpixel_in_S((t >> 2) & 1, t & 1, kw)) acc += v[t];
+                dw3[co * s_co + ci * s_ci + (kh * 3 + kw) * s_tap] += acc;
+            }
+    }
+}
+
+DMVAE_API int dmvae_subpixel_fold_wgrad(const float* dwp, float* dw3, int64_t stride_co, int64_t stride_ci, int64_t stride_tap, int Cout,
+                                        int Cin, void* stream) {
+    DMVAE_CHECK_ARG(dwp && dw3, "subpixel_fold_wgrad: null pointer");
+    DMVAE_CHECK_ARG(Cout > 0 && Cin > 0, "subpixel_fold_wgrad: bad shape");
+    subpixel_fold_wgrad_kernel<<<ew_grid((int64_t)Cout * Cin), 256, 0, (cudaStream_t)stream>>>(dwp, dw3, stride_co, stride_ci, stride_tap, Cout, Cin);
+    DMVAE_CHECK_LAUNCH("subpixel_fold_wgrad_kernel");
+    return DMVAE_OK;
+}
+
 // ---- gradient patches of a thin output (the C->3 head) ---------------------------------------------------------------
 // P[pixel][j], j = tap*Cout + co  (padded with zeros to 32 columns):  P[p][j] = dy[p - offset(tap)][co], zero outside.
 // With it both gradients of a "same" conv with a handful of output channels become plain 1x1 GEMMs on the tcgen05 tiles:

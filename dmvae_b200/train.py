@@ -279,6 +279,13 @@ class TokenizerTrainer:
     def graphed(self) -> bool:
         return self._section is not None
 
+    def weights_changed(self) -> None:
+        """Call after writing the trainable weights out of band (``load_state_dict``, ``load_pretrained``, manual edits) once the
+        trainer exists: bumps the version counters and rebuilds the optimizer-maintained bf16 operand copies that a captured CUDA
+        graph reads directly (an eager step would notice the stale version stamp by itself; a replayed graph cannot)."""
+        torch.autograd.graph.increment_version(self.params)
+        self.fused.sync_w16()
+
     def step(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
         if self._section is not None and images.shape == self._gx.shape:
             self._gx.copy_(images, non_blocking=True)

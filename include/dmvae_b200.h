@@ -34,7 +34,7 @@ extern "C" {
 
 /* Bumped whenever a prototype below changes; the ctypes binding (dmvae_b200/_lib.py) refuses a library whose
  * dmvae_abi_version() differs from the table it was written against. */
-#define DMVAE_ABI_VERSION 3
+#define DMVAE_ABI_VERSION 4
 
 const char* dmvae_last_error(void);
 int dmvae_abi_version(void);
@@ -145,6 +145,27 @@ int dmvae_conv_tc_wgrad_strided(const void* x, const void* dy, float* dw_tap_maj
                                 void* stream);
 /* dyz[b][2oh+1][2ow+1][c] = dy[b][oh][ow][c], zero elsewhere (bf16, C % 8 == 0). */
 int dmvae_zero_insert2x(const void* dy, void* dyz, int64_t B, int OH, int OW, int C, void* stream);
+
+/* Sub-pixel form of flux_ae.Upsample (models/flux_ae.py:98-107: F.interpolate(scale_factor=2, "nearest") + 3x3 conv): every
+ * output phase (py, px) is a 2x2 conv on the LOW-RES input whose taps are sums of the 3x3 taps falling on the same input pixel --
+ * 16 instead of 36 tap-GEMMs per low-res pixel, no 4x larger intermediate.  H, W below are the LOW-RES size; x [B][H][W][Cin],
+ * y / dy [B][2H][2W][Cout]; Cin, Cout multiples of 256, W % 8 == 0, H % 16 == 0.
+ *   dmvae_subpixel_pack        w3 (fp32, any element strides) -> wp_fwd[16][Cout][Cin], wp_dgrad[16][Cin][Cout] (bf16)
+ *   dmvae_conv_up2x_fwd        y = conv(nearest2x(x)) + bias (+ GroupNorm statistics of y, as dmvae_conv_tc_fwd)
+ *   dmvae_conv_up2x_dgrad      dx from dy (all four phases accumulated in one tile; dy sampled with TMA element stride 2)
+ *   dmvae_conv_up2x_wgrad      dwp[16][Cout][Cin] (fp32) += per-phase-tap gradients
+ *   dmvae_subpixel_fold_wgrad  dw3 (fp32, any element strides) += fold of dwp onto the nine 3x3 taps
+ * Summing taps before the bf16 rounding changes the rounding points relative to the reference (one rounding of the tap sum
+ * instead of one per tap): same bf16-level tolerance as every conv here, but not the same bits as the two-kernel form. */
+int dmvae_conv_up2x_supported(int B, int H, int W, int Cin, int Cout);
+int dmvae_subpixel_pack(const float* w3, int64_t stride_co, int64_t stride_ci, int64_t stride_tap, void* wp_fwd, void* wp_dgrad,
+                        int Cout, int Cin, void* stream);
+int dmvae_conv_up2x_fwd(const void* x, const void* wp_fwd, const float* bias, void* y, double* gn_stats, int B, int H, int W,
+                        int Cin, int Cout, void* stream);
+int dmvae_conv_up2x_dgrad(const void* dy, const void* wp_dgrad, void* dx, int B, int H, int W, int Cin, int Cout, void* stream);
+int dmvae_conv_up2x_wgrad(const void* x, const void* dy, float* dwp, int B, int H, int W, int Cin, int Cout, void* stream);
+int dmvae_subpixel_fold_wgrad(const float* dwp, float* dw3, int64_t stride_co, int64_t stride_ci, int64_t stride_tap, int Cout,
+                              int Cin, void* stream);
 
 /* Tuning / test hook (host only, process-wide).  The conv entry points pick a tile per shape:
  *   3x3, Cout % 256 == 0 ........ halo-resident CTA pair (one TMA halo serves all nine taps, cta_group::2, N = 256)

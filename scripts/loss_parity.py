@@ -73,7 +73,7 @@ def _force_weights(tr, vae, arm, world):
                     p.copy_(src[name])
     if world > 1:
         dist.broadcast(tr.fused.flat_p, src=0)
-    torch.autograd.graph.increment_version(tr.params)
+    tr.weights_changed()                           # out-of-band weight write: refresh the optimizer-maintained bf16 operands
 
 
 def run_parity(dev, steps=100, global_batch=16, size="large", cuda_graph=True, micro=4, lr=1e-4, seed=1234, free_running=True):

@@ -104,6 +104,18 @@ def main():
                 res["fwd_halo_res_tflops"] = round(flops / us / 1e6, 1)
                 del rsd
                 _lib.query("dmvae_conv_tc_set_tile_mode", 7)
+            # the tile the dispatcher picks by itself: plain, with the fused GroupNorm statistics, with residual + statistics (what
+            # the decoder's conv1 / conv2 launch), with the ReLU epilogue and the ReLU-gated data gradient (the VGG16 launches)
+            pad = ((k - 1) // 2, (k - 1) // 2)
+            rsd = torch.randn(B, hw, hw, cout, device=DEV).bfloat16()
+            msk = torch.relu(torch.randn(B, hw, hw, cout, device=DEV)).bfloat16()
+            variants = {"auto": dict(), "auto_stats": dict(want_gn_stats=True), "auto_res_stats": dict(residual=rsd, want_gn_stats=True),
+                        "auto_relu": dict(flags=ops.EPI_RELU), "auto_mask": dict(residual=msk, flags=ops.EPI_MASK)}
+            for name, kw in variants.items():
+                r = kw.pop("residual", None)
+                us = timeit(lambda i: ops.conv_forward_raw(x, wf, bias, r, k, k, 1, pad, **kw), a.iters, 1)
+                res[f"fwd_{name}_tflops"] = round(flops / us / 1e6, 1)
+            del rsd, msk
             us = timeit(lambda i: ops.conv_wgrad_raw(x, dy, k, k, 1, ((k - 1) // 2, (k - 1) // 2)), a.iters, 1)
             res["wgrad_tflops"] = round(flops / us / 1e6, 1)
             if cin <= 128 and cout < 256:
@@ -113,6 +125,37 @@ def main():
                     res[f"wgrad_tpc{m - 10}_tflops"] = round(flops / us / 1e6, 1)
                 _lib.query("dmvae_conv_tc_set_tile_mode", 13)
             print(json.dumps({"kernel": "conv_tc", "cin": cin, "cout": cout, "hw": hw, "k": k, "gflop": round(flops / 1e9, 1), **res}), flush=True)
+            del x, dy
+            torch.cuda.empty_cache()
+
+    if want("upconv"):
+        # flux_ae.Upsample: nearest 2x + 3x3.  Two-kernel form (upsample2x + hi-res conv) vs the sub-pixel form, all three passes;
+        # "tflops" are algorithmic FLOPs of the REFERENCE op (36 tap-GEMMs per low-res pixel) / time, so the two forms compare directly
+        for c, hw in ((512, 32), (512, 64), (256, 128)):
+            B = 16
+            x = torch.randn(B, hw, hw, c, device=DEV).bfloat16().requires_grad_(True)
+            w = (torch.randn(c, c, 3, 3, device=DEV) * 0.02).requires_grad_(True)
+            bias = torch.zeros(c, device=DEV, requires_grad=True)
+            dy = torch.randn(B, 2 * hw, 2 * hw, c, device=DEV).bfloat16()
+            flops = 2.0 * B * 4 * hw * hw * c * c * 9
+            pk, sp = ops.WeightPack(), ops.SubpixelPack()
+            res = {}
+
+            def plain_f(i):
+                return ops.conv2d(ops.upsample2x(x), w, bias, pk, want_gn_stats=True)
+
+            def sub_f(i):
+                return ops.upsample_conv(x, w, bias, sp, True)
+            for name, f in (("two_kernel", plain_f), ("subpixel", sub_f)):
+                us_f = timeit(f, a.iters, 1)
+                y = f(0)
+                us_b = timeit(lambda i: torch.autograd.grad(y, [x, w, bias], dy, retain_graph=True), a.iters, 1)
+                res[f"{name}_fwd_us"] = round(us_f, 1)
+                res[f"{name}_bwd_us"] = round(us_b, 1)
+                res[f"{name}_fwd_ref_tflops"] = round(flops / us_f / 1e6, 1)
+                res[f"{name}_bwd_ref_tflops"] = round(2 * flops / us_b / 1e6, 1)
+                del y
+            print(json.dumps({"kernel": "upsample_conv", "c": c, "hw_in": hw, "ref_gflop_fwd": round(flops / 1e9, 1), **res}), flush=True)
             del x, dy
             torch.cuda.empty_cache()
 
