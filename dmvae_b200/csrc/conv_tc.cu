@@ -1586,6 +1586,14 @@ int get_tensor_map(const void* ptr, int rank, const uint64_t* dims, const uint32
     }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return dmvae_set_error(DMVAE_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    // cuTensorMapEncodeTiled is a driver call and needs a current context on THIS thread; an autograd worker thread that has not
+    // issued a runtime call through this library yet may have none (CUDA_ERROR_INVALID_CONTEXT).  Bind the primary context of the
+    // device that owns the tensor (not "device 0": one process per GPU, but the rank's GPU need not be ordinal 0).
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) cudaSetDevice(at.device);
+        else cudaGetLastError();
+    }
     cuuint64_t gdim[4]; cuuint64_t gstride[3]; cuuint32_t bdim[4]; cuuint32_t estride[4];
     uint64_t stride = 2;
     for (int i = 0; i < rank; ++i) {

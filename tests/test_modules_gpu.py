@@ -414,8 +414,8 @@ def test_optimizer_maintained_weight_packs_and_tap_major_arena():
     wf, wd = packs[id(w3)].get(w3)
     rf, rd = plain(w3)
     assert wf.data_ptr() != w3._dmvae_w16.data_ptr() and torch.equal(wf, rf) and torch.equal(wd, rd)
-    opt.sync_w16()
-    wf, _ = packs[id(w3)].get(w3)
+    opt.sync_w16()                                                        # the copy is current again: a pack built now picks it up
+    wf, _ = ops.WeightPack().get(w3)
     assert wf.data_ptr() == w3._dmvae_w16.data_ptr() and torch.equal(wf, rf)
     # checkpoint surface
     sd = net.state_dict()
