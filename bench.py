@@ -128,7 +128,20 @@ def _work(name, a):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def build_trainer(device, model_size="large", z_channels=32):
+def patchgan_standin():
+    """A PatchGAN-shaped discriminator in stock PyTorch (4x4 stride-2 conv stack, 64-128-256-512 channels, BatchNorm, LeakyReLU)
+    for the GAN workload: the reference's discriminators (models/patchgan.py, models/dinodisc.py) are black boxes outside the
+    accelerated path; what the workload exercises is the adaptive-weight generator branch through the decoder."""
+    nn = torch.nn
+    layers, c = [nn.Conv2d(3, 64, 4, 2, 1), nn.LeakyReLU(0.2)], 64
+    for cout, stride in ((128, 2), (256, 2), (512, 1)):
+        layers += [nn.Conv2d(c, cout, 4, stride, 1, bias=False), nn.BatchNorm2d(cout), nn.LeakyReLU(0.2)]
+        c = cout
+    layers += [nn.Conv2d(c, 1, 4, 1, 1)]
+    return nn.Sequential(*layers)
+
+
+def build_trainer(device, model_size="large", z_channels=32, gan=False):
     from dmvae_b200.lpips import LPIPS
     from dmvae_b200.train import LossConfig, TokenizerTrainer, VAELossFunction
     from dmvae_b200.vae import VAE
@@ -142,8 +155,9 @@ def build_trainer(device, model_size="large", z_channels=32):
         warnings.simplefilter("ignore")
         lp = LPIPS(ckpt_path=os.path.join(ROOT, "ckpt_vae", "vgg.pth") if os.path.exists(os.path.join(ROOT, "ckpt_vae", "vgg.pth")) else None,
                    pretrained_vgg=False).eval().to(device)
-    cfg = LossConfig(l1=1.0, l2=0.0, lpips=1.0, dmd_weight=0.0)
-    return TokenizerTrainer(vae, VAELossFunction(cfg, lpips_loss=lp), lr=1e-4)
+    cfg = LossConfig(l1=1.0, l2=0.0, lpips=1.0, dmd_weight=0.0, disc_weight=0.5 if gan else 0.0)
+    disc = patchgan_standin().to(device) if gan else None
+    return TokenizerTrainer(vae, VAELossFunction(cfg, lpips_loss=lp, disc=disc), lr=1e-4)
 
 
 class Stress512Trainer:
@@ -224,6 +238,9 @@ WORKLOADS = {
                  "fwd+bwd, L1+LPIPS(VGG16), allreduce, clip, AdamW, EMA",
     "stress512": "BASELINE configs[4] stress: flux_ae Encoder -> reparam+KL -> Decoder fwd+bwd at 512x512, L1 + KL, "
                  "allreduce, clip, AdamW, EMA",
+    "gan": "BASELINE configs[3]: the tokenizer step with the GAN generator branch (adaptive weight: two partial autograd.grad calls "
+           "on decoder.conv_out.weight, train_dmd.py:244-257) and the discriminator's hinge step; PatchGAN-shaped stock-PyTorch "
+           "discriminator stand-in",
     "dmd": "train_dmd.py iteration (BASELINE configs[2]): LightningDiT-Mini/1 teacher+student; every 5th iteration is a VAE "
            "turn (trainable ViT-L/16 encoder + flux Decoder fwd+bwd, L1+LPIPS+10*DMD cfg 5), every iteration a student "
            "flow-matching step; allreduce, clip, AdamW per network; steps rounded up to whole 5-iteration cycles",
@@ -382,7 +399,7 @@ def run_ours(args):
         if args.steps % tr.every:
             args.steps += tr.every - args.steps % tr.every        # whole vae_train_every cycles inside the timed region
     else:
-        tr = build_trainer(dev)
+        tr = build_trainer(dev, gan=args.workload == "gan")
     g = torch.Generator().manual_seed(42 * world + rank)
     graphed = False
     exchange_mode = "eager"
@@ -393,7 +410,7 @@ def run_ours(args):
     for i in range(args.warmup if args.workload != "dmd" else 2 * tr.every):
         tr.step(resident[i % n_pool])
     graph_launches = None
-    if args.cuda_graph and args.workload == "tokenizer":
+    if args.cuda_graph and args.workload in ("tokenizer", "gan"):
         # launches a replay stands for: an eager pass with the weight re-packs included (version counters bumped)
         torch.autograd.graph.increment_version(tr.params)
         _lib.Stats.reset()
@@ -632,7 +649,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="main timing only: no dmd_stage / loss_parity / gpu_baseline / cpu_baseline")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                     help="tokenizer workload: issue every kernel from Python instead of replaying forward+backward from a CUDA graph")
-    ap.add_argument("--workload", default="tokenizer", choices=["tokenizer", "stress512", "dmd"],
+    ap.add_argument("--workload", default="tokenizer", choices=["tokenizer", "stress512", "dmd", "gan"],
                     help="tokenizer = BASELINE configs[1] (the headline workload); dmd = configs[2]; stress512 = configs[4] "
                          "(no CPU baseline for the last two)")
     args = ap.parse_args()

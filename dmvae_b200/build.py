@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdmvae_b200.so")
-SOURCES = ["api.cu", "losses.cu", "groupnorm.cu", "layout.cu", "conv_direct.cu", "conv_tc.cu", "optim.cu", "pool.cu"]
+SOURCES = ["api.cu", "losses.cu", "groupnorm.cu", "layout.cu", "conv_direct.cu", "conv_tc.cu", "optim.cu", "pool.cu", "dit_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static",

@@ -3,7 +3,11 @@
 A stock-PyTorch restatement of ``diffusion/lightningdit/lightningdit.py`` (RMSNorm, QK-norm, 2-D RoPE, SwiGLU, adaLN)
 under the reference's parameter names, so LightningDiT checkpoints (``model`` / ``ema`` entries) load with ``strict=True``.
 On the hot path these networks are black-box producers of v_teacher / v_student (4 no-grad forwards per VAE turn,
-train_dmd.py:212-217); no hand-written kernel lives here yet.  What this module adds over the reference:
+train_dmd.py:212-217).  What this module adds over the reference:
+
+* under ``no_grad`` + ``autocast(bf16)`` on a GPU (exactly those scoring passes) the elementwise chains around the GEMMs run as two
+  library kernels -- RMSNorm + adaLN modulate -> bf16, and QK-norm + 2-D RoPE + head split -> bf16 (csrc/dit_ops.cu) -- in place
+  of the reference's ``@torch.compile`` sites; the autograd path (the student's training step) is the stock-PyTorch restatement;
 
 * ``forward_cond_uncond``: the conditional and the unconditional pass of classifier-free guidance as ONE batched forward
   (2B rows) instead of two, halving launches for the DMD loss (train_dmd.py:214-217 calls the model twice);
@@ -19,6 +23,26 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+from ._lib import call, dtype_code, ptr
+
+
+def _fused_ok(x: torch.Tensor) -> bool:
+    """The no-grad scoring passes of the DMD loss on a GPU under autocast(bf16): the fused glue kernels apply."""
+    return (x.is_cuda and not torch.is_grad_enabled() and torch.is_autocast_enabled()
+            and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+
+
+def rmsnorm_modulate(norm: "RMSNorm", x: torch.Tensor, shift, scale) -> torch.Tensor:
+    """modulate(norm(x), shift, scale) -> bf16 in one kernel; shift / scale: (B, D) bf16 views of the adaLN output (or None)."""
+    B, N, D = x.shape
+    x = x.contiguous()
+    y = torch.empty((B, N, D), dtype=torch.bfloat16, device=x.device)
+    ref = scale if scale is not None else shift
+    stride = ref.stride(0) if ref is not None else 0
+    call("dmvae_rmsnorm_modulate", ptr(x), dtype_code(x), ptr(norm.weight), ptr(shift), ptr(scale), stride, ptr(y), B * N, N, D,
+         float(norm.eps))
+    return y
 
 
 def modulate(x, shift, scale):
@@ -79,6 +103,18 @@ class Attention(nn.Module):
 
     def forward(self, x, rope=None):
         B, N, C = x.shape
+        if (_fused_ok(x) and isinstance(self.q_norm, (RMSNorm, nn.Identity)) and type(self.q_norm) is type(self.k_norm)
+                and self.head_dim % 2 == 0 and self.head_dim <= 192):
+            qkv = self.qkv(x)                               # bf16 under autocast, (B, N, 3*C) = [B][N][3][H][hd]
+            if qkv.dtype == torch.bfloat16 and qkv.is_contiguous():
+                H, hd = self.num_heads, self.head_dim
+                q, k, v = (torch.empty((B, H, N, hd), dtype=torch.bfloat16, device=x.device) for _ in range(3))
+                qn = isinstance(self.q_norm, RMSNorm)
+                call("dmvae_qk_norm_rope", ptr(qkv), ptr(self.q_norm.weight) if qn else None, ptr(self.k_norm.weight) if qn else None,
+                     ptr(rope.freqs_cos) if rope is not None else None, ptr(rope.freqs_sin) if rope is not None else None,
+                     ptr(q), ptr(k), ptr(v), B, N, H, hd, float(self.q_norm.eps) if qn else 0.0)
+                o = F.scaled_dot_product_attention(q, k, v)
+                return self.proj(o.transpose(1, 2).reshape(B, N, C))
         q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4).unbind(0)
         q, k = self.q_norm(q), self.k_norm(k)
         if rope is not None:
@@ -161,6 +197,9 @@ class LightningDiTBlock(nn.Module):
             shift_msa = shift_mlp = None
         else:
             shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = m.chunk(6, dim=1)
+        if _fused_ok(x) and isinstance(self.norm1, RMSNorm) and x.shape[-1] in (256, 768, 1152) and scale_msa.dtype == torch.bfloat16:
+            x = x + gate_msa.unsqueeze(1) * self.attn(rmsnorm_modulate(self.norm1, x, shift_msa, scale_msa), rope=feat_rope)
+            return x + gate_mlp.unsqueeze(1) * self.mlp(rmsnorm_modulate(self.norm2, x, shift_mlp, scale_mlp))
         x = x + gate_msa.unsqueeze(1) * self.attn(modulate(self.norm1(x), shift_msa, scale_msa), rope=feat_rope)
         return x + gate_mlp.unsqueeze(1) * self.mlp(modulate(self.norm2(x), shift_mlp, scale_mlp))
 
@@ -176,6 +215,8 @@ class FinalLayer(nn.Module):
 
     def forward(self, x, c):
         shift, scale = self.adaLN_modulation(c).chunk(2, dim=1)
+        if _fused_ok(x) and isinstance(self.norm_final, RMSNorm) and x.shape[-1] in (256, 768, 1152) and scale.dtype == torch.bfloat16:
+            return self.linear(rmsnorm_modulate(self.norm_final, x, shift, scale))
         return self.linear(modulate(self.norm_final(x), shift, scale))
 
 

@@ -52,19 +52,30 @@ class LossConfig:
     t0: float = 0.0
     t1: float = 1.0
     time_dist_shift: float = 1.0
+    disc_weight: float = 0.0
+    disc_start_step: int = 0
+    bcr: float = 0.0
 
 
 class VAELossFunction:
-    """Generator-side losses of the reference's VAELossFunction.  ``base_model`` (teacher, s_real) and ``sit``
-    (student, s_fake) are black-box callables ``v = model(xt, t, labels)`` (LightningDiT in the reference)."""
+    """The reference's VAELossFunction (train_dmd.py:169-285).  ``base_model`` (teacher, s_real) and ``sit`` (student, s_fake)
+    are black-box callables ``v = model(xt, t, labels)`` (LightningDiT in the reference); ``disc`` is a black-box discriminator
+    ``logits = disc(images)`` (DinoDisc / PatchGAN in the reference: stock PyTorch, out of scope for kernels -- SURVEY section 2),
+    ``last_layer`` the tensor the adaptive GAN weight is measured on (``vae.decoder.get_last_layer()``, :247), ``aug`` /
+    ``bcr_aug`` the differentiable augmentations applied to the discriminator input (DiffAug, :199-200; identity when None)."""
 
     def __init__(self, args: LossConfig, lpips_loss: Optional[nn.Module] = None, sit: Optional[Callable] = None,
-                 base_model: Optional[Callable] = None):
+                 base_model: Optional[Callable] = None, disc: Optional[nn.Module] = None, last_layer: Optional[torch.Tensor] = None,
+                 aug: Optional[Callable] = None, bcr_aug: Optional[Callable] = None):
         self.args = args
         self.lpips_loss = lpips_loss
         self.l1, self.l2, self.lpips, self.dmd_weight = args.l1, args.l2, args.lpips, args.dmd_weight
+        self.disc_weight, self.bcr_weight = args.disc_weight, args.bcr
         self.sit_wo_ddp = sit
         self.base_model = base_model
+        self.disc, self.last_layer = disc, last_layer
+        self.aug = aug if aug is not None else (lambda x, fade=0.0: x)
+        self.bcr_aug = bcr_aug if bcr_aug is not None else (lambda x, fade=0.0: x)
 
     def compute_distribution_matching_loss(self, latents_norm: torch.Tensor, labels: torch.Tensor, step: int = 0,
                                            cpu_generator: Optional[torch.Generator] = None,
@@ -100,7 +111,7 @@ class VAELossFunction:
         return loss, {"dmd_loss": loss.detach(), "dmd_gradient_norm": gnorm}
 
     def forward_generator(self, images_pm1, recon_image, latents=None, labels=None, compute_dmd=False, step=0, t=None):
-        """train_dmd.py:233-262 without the discriminator branch."""
+        """train_dmd.py:233-262.  Log values are device scalars (the reference calls .item() on each: six host syncs per step)."""
         l1, l2 = losses.l1_l2_loss(recon_image, images_pm1)
         rec_loss = l1 * self.l1 + l2 * self.l2
         log = {"L1": l1.detach(), "L2": l2.detach()}
@@ -109,11 +120,45 @@ class VAELossFunction:
             rec_loss = rec_loss + lp * self.lpips
             log["LPIPS"] = lp.detach()
         log["rec_loss"] = rec_loss.detach()
+        if self.disc is not None and self.disc_weight > 0 and step >= self.args.disc_start_step:
+            # :244-257 -- adaptive GAN weight: ratio of the two losses' gradient norms at the decoder's last layer.  The two partial
+            # autograd.grad calls run through the custom Functions with retain_graph=True (saved tensors are never written in
+            # place) and outside GradArena.direct(), so they return tensors instead of accumulating into the arena.
+            self.disc.eval()
+            for p in self.disc.parameters():
+                p.requires_grad = False
+            d_loss = -self.disc(self.aug(recon_image, 0)).mean()
+            g_rec = torch.autograd.grad(rec_loss, self.last_layer, retain_graph=True)[0]
+            g_gan = torch.autograd.grad(d_loss, self.last_layer, retain_graph=True)[0]
+            w = (g_rec.detach().norm() / g_gan.detach().norm().add_(1e-6)).clamp_(0.0, 1e4)
+            d_weight = self.disc_weight * w
+            rec_loss = rec_loss + d_loss * d_weight
+            log["d_weight"] = d_weight.detach()
         if compute_dmd:
             dmd, dmd_log = self.compute_distribution_matching_loss(latents, labels, step, t=t)
             log.update(dmd_log)
             rec_loss = rec_loss + dmd * self.dmd_weight
         return rec_loss, log
+
+
+    def forward_discriminator(self, images_pm1, recon_image, fade_blur_schedule=0.0):
+        """train_dmd.py:265-285: hinge loss on real / reconstructed images + balanced consistency regularisation."""
+        for p in self.disc.parameters():
+            p.requires_grad = True
+        self.disc.train()
+        bs = images_pm1.size(0)
+        both = torch.cat([images_pm1, recon_image], dim=0)
+        logits = self.disc(self.aug(both, fade_blur_schedule)).float()
+        logits_real, logits_fake = logits[:bs], logits[bs:]
+        d_loss = 0.5 * (torch.relu(1.0 - logits_real).mean() + torch.relu(1.0 + logits_fake).mean())
+        log = {"d_loss": d_loss.detach(), "acc_real": (logits_real.detach() > 0).float().mean() * 100,
+               "acc_fake": (logits_fake.detach() < 0).float().mean() * 100}
+        if self.bcr_weight > 0:
+            logits2 = self.disc(self.bcr_aug(both, 0.0)).float()
+            lbcr = nn.functional.mse_loss(logits2, logits) * self.bcr_weight
+            log["bcr_loss"] = lbcr.detach()
+            d_loss = d_loss + lbcr
+        return d_loss, log
 
 
 from .train_arena import GradArena  # noqa: E402,F401  (re-exported)
@@ -219,10 +264,13 @@ class _PinnedTimes:
 
 
 class TokenizerTrainer:
-    """One VAE-pretrain step of train_tokenizer.py:403-437 (frozen encoder, recon losses, clip, AdamW, EMA)."""
+    """One VAE-pretrain step of train_tokenizer.py:403-437 (frozen encoder, recon losses, clip, AdamW, EMA).  When the loss
+    function carries a discriminator (``loss_fn.disc``, BASELINE configs[3]) the step is the full GAN iteration: generator branch
+    with the adaptive weight (:179-199), then the discriminator's hinge step on (images, recon.detach()) (:420-428) with its own
+    arena / fused optimizer -- the discriminator itself is whatever stock-PyTorch module the caller hands in."""
 
     def __init__(self, vae: nn.Module, loss_fn: VAELossFunction, lr: float = 1e-4, wd: float = 0.0, ema: bool = True,
-                 clip: float = 1.0):
+                 clip: float = 1.0, lr_disc: float = 1e-4):
         from .optim import FlatAdamWEMA
         self.vae = vae
         self.loss_fn = loss_fn
@@ -231,6 +279,16 @@ class TokenizerTrainer:
         self.params = self.arena.params
         self.fused = FlatAdamWEMA(self.params, lr=lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd, max_norm=clip,
                                   ema_decay=0.9999 if ema else None, arena=self.arena)
+        self.arena_disc = self.fused_disc = None
+        self.global_step = 0
+        if loss_fn.disc is not None and loss_fn.disc_weight > 0:
+            for p in loss_fn.disc.parameters():
+                p.requires_grad = True
+            self.arena_disc = GradArena(loss_fn.disc.parameters())
+            self.fused_disc = FlatAdamWEMA(self.arena_disc.params, lr=lr_disc, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd,
+                                           max_norm=clip, ema_decay=None, arena=self.arena_disc)
+            if loss_fn.last_layer is None:
+                loss_fn.last_layer = vae.decoder.get_last_layer()
         self._section: Optional[_GraphedSection] = None
         self._exchange_outside = True       # eager: _forward_backward ends with the exchange itself
         self.exchange_mode = "eager"
@@ -239,12 +297,20 @@ class TokenizerTrainer:
         self.arena.zero()
         with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
             recon = self.vae(images, freeze_encoder=True)
-            loss, log = self.loss_fn.forward_generator(images, recon)
+            loss, log = self.loss_fn.forward_generator(images, recon, step=self.global_step)
         with self.arena.direct():                   # conv / GroupNorm gradients accumulate straight into the arena
             loss.backward()
         if exchange:
             self.arena.allreduce()                  # chunks not yet launched from the hooks, wait, (average inside NCCL)
         log["loss"] = loss.detach()
+        if self.arena_disc is not None and self.global_step >= self.loss_fn.args.disc_start_step:
+            self.arena_disc.zero()
+            with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
+                d_loss, d_log = self.loss_fn.forward_discriminator(images, recon.detach())
+            d_loss.backward()
+            if exchange:
+                self.arena_disc.allreduce()
+            log.update(d_log)
         return log
 
     def capture_cuda_graph(self, example_images: torch.Tensor, warmup: int = 2, strict: bool = False) -> bool:
@@ -261,7 +327,8 @@ class TokenizerTrainer:
 
             def body():                             # hooks off (fallback capture) = the exchange is issued after each replay
                 return self._forward_backward(self._gx, exchange=self.arena.hooks_enabled)
-            self._section, self.exchange_mode = _capture_with_exchange(body, [self.arena], self.params, warmup, (self.fused,))
+            arenas = [self.arena] + ([self.arena_disc] if self.arena_disc is not None else [])
+            self._section, self.exchange_mode = _capture_with_exchange(body, arenas, self.params, warmup, (self.fused,))
             self._exchange_outside = self.exchange_mode == "post-replay"
             return True
         except Exception as e:                      # noqa: BLE001
@@ -292,9 +359,14 @@ class TokenizerTrainer:
             log = self._section.replay()
             if self._exchange_outside:
                 self.arena.allreduce()
+                if self.arena_disc is not None:
+                    self.arena_disc.allreduce()
         else:
             log = self._forward_backward(images)
         log["vae_norm"] = self.fused.step()         # clip + AdamW + EMA in two kernels over the flat arenas
+        if self.fused_disc is not None and "d_loss" in log:
+            log["disc_norm"] = self.fused_disc.step()
+        self.global_step += 1
         return log
 
 

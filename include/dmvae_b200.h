@@ -34,7 +34,7 @@ extern "C" {
 
 /* Bumped whenever a prototype below changes; the ctypes binding (dmvae_b200/_lib.py) refuses a library whose
  * dmvae_abi_version() differs from the table it was written against. */
-#define DMVAE_ABI_VERSION 4
+#define DMVAE_ABI_VERSION 5
 
 const char* dmvae_last_error(void);
 int dmvae_abi_version(void);
@@ -236,6 +236,19 @@ int dmvae_relu_mask(const void* y, const void* dy, void* out, int64_t n, void* s
  *   next Linear casts its input to bf16). */
 int dmvae_scale_residual(float* x, const void* y_bf16, const float* gamma, int64_t rows, int D, void* stream);
 int dmvae_layernorm_bf16(const float* x, const float* weight, const float* bias, void* y_bf16, int64_t rows, int D, float eps, void* stream);
+
+/* ------------------------------------------------------------------ N1: LightningDiT glue (no-grad scoring passes) ---- */
+/* The teacher / student velocity networks are evaluated without autograd four times per VAE turn (train_dmd.py:212-217); the
+ * reference runs their elementwise chains through @torch.compile (diffusion/lightningdit/lightningdit.py:27,135,165,241,269).
+ * dmvae_rmsnorm_modulate: y (bf16) = RMSNorm(x) * (1 + scale[b]) + shift[b] -- `modulate(norm(x), shift, scale)` of
+ *   lightningdit.py:27-31,243-249 over rms_norm.py:34-77; shift / scale are bf16 rows of the adaLN output (row b at element
+ *   offset b * mod_stride), either may be NULL; D in {256, 768, 1152}.
+ * dmvae_qk_norm_rope: the qkv Linear's output [B][N][3][H][hd] -> q, k (RMSNorm over hd, then the 2-D rotary embedding of
+ *   pos_embed.py:96-134) and v, each [B][H][N][hd] bf16, ready for SDPA (lightningdit.py:70-85). */
+int dmvae_rmsnorm_modulate(const void* x, int x_dtype, const float* weight, const void* shift, const void* scale, int64_t mod_stride,
+                           void* y, int64_t rows, int tokens, int D, float eps, void* stream);
+int dmvae_qk_norm_rope(const void* qkv, const float* wq, const float* wk, const float* cos_tab, const float* sin_tab, void* q, void* k,
+                       void* v, int64_t B, int N, int H, int hd, float eps, void* stream);
 
 /* ------------------------------------------------------------------ N2: fused optimizer step ---------------- */
 /* Replaces clip_grad_norm_ + AdamW.step + update_ema (train_tokenizer.py:140-150,415-417,437; train_dmd.py:540-544) on

@@ -205,6 +205,60 @@ def test_tokenizer_trainer_steps_and_loss_goes_down():
     assert last < first
 
 
+def _tiny_disc():
+    """A PatchGAN-shaped stand-in (stock PyTorch; the reference's discriminators are out of scope for kernels)."""
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 32, 4, 2, 1), torch.nn.LeakyReLU(0.2), torch.nn.Conv2d(32, 64, 4, 2, 1),
+                               torch.nn.BatchNorm2d(64), torch.nn.LeakyReLU(0.2), torch.nn.Conv2d(64, 1, 4, 1, 1))
+
+
+def test_gan_iteration_adaptive_weight_eager_and_graph():
+    """BASELINE configs[3]: recon + LPIPS + GAN with the adaptive weight (train_dmd.py:244-257: two partial autograd.grad calls on
+    decoder.conv_out.weight with retain_graph=True before the real backward) and the discriminator's hinge step (:265-285), through
+    the custom Functions -- eagerly and replayed from a CUDA graph.  The adaptive weight is checked against its definition."""
+    from dmvae_b200.vae import VAE
+    from dmvae_b200.lpips import LPIPS
+    from dmvae_b200.train import LossConfig, TokenizerTrainer, VAELossFunction
+
+    def make():
+        torch.manual_seed(0)
+        vae = VAE(z_channels=32, model_size="base").to(DEV)
+        vae.encoder.eval()
+        for p in vae.encoder.parameters():
+            p.requires_grad = False
+        lp = LPIPS(ckpt_path=None, pretrained_vgg=False).eval().to(DEV)
+        disc = _tiny_disc().to(DEV)
+        fn = VAELossFunction(LossConfig(disc_weight=0.5, bcr=0.0), lpips_loss=lp, disc=disc)
+        return vae, disc, fn, TokenizerTrainer(vae, fn, lr=2e-4)
+
+    g = torch.Generator(device=DEV).manual_seed(9)
+    xs = [torch.rand(2, 3, 256, 256, device=DEV, generator=g) * 2 - 1 for _ in range(3)]
+    vae, disc, fn, tr = make()
+    # the weight by its definition, from separate graphs
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        recon = vae(xs[0], freeze_encoder=True)
+        rec, _ = VAELossFunction(LossConfig(), lpips_loss=fn.lpips_loss).forward_generator(xs[0], recon)
+        disc.eval()
+        gan = -disc(recon).mean()
+    W = vae.decoder.get_last_layer()
+    g_rec = torch.autograd.grad(rec, W, retain_graph=True)[0]
+    g_gan = torch.autograd.grad(gan, W)[0]
+    expect = 0.5 * (g_rec.norm() / (g_gan.norm() + 1e-6)).clamp(0, 1e4)
+    d0 = disc[0].weight.detach().clone()
+    log = tr.step(xs[0])
+    assert abs(log["d_weight"].item() - expect.item()) < 2e-2 * expect.item(), (log["d_weight"].item(), expect.item())
+    for k in ("loss", "d_loss", "acc_real", "acc_fake", "vae_norm", "disc_norm"):
+        assert torch.isfinite(log[k]).all(), k
+    assert not torch.equal(disc[0].weight, d0)                    # the discriminator stepped
+    # graph replay trains like the eager path
+    _, _, _, eager = make()
+    _, _, _, graphed = make()
+    assert graphed.capture_cuda_graph(xs[0], strict=True)
+    for x in xs:
+        le, lg = eager.step(x), graphed.step(x)
+        assert abs(le["loss"].item() - lg["loss"].item()) <= 2e-2 * abs(le["loss"].item())
+        assert abs(le["d_loss"].item() - lg["d_loss"].item()) <= 2e-2 * abs(le["d_loss"].item()) + 1e-3
+
+
 def test_loss_curve_parity_real_trainer_vs_stock_arms():
     """12 steps of the REAL TokenizerTrainer (CUDA-graph replay, arena, fused clip + AdamW + EMA; ViT-B encoder, production decoder)
     against the strict-fp32 stock-PyTorch anchor and the cuDNN-autocast control arm (scripts/loss_parity.py, scripts/stock_arms.py).
@@ -464,6 +518,40 @@ def test_dmd_stage_iteration_with_lightningdit():
     assert not torch.equal(vae.encoder.model.blocks[0].attn.qkv.weight, e0)    # encoder is trainable in the DMD stage (:519)
     log2 = tr.step(x, y, vae_turn=False)
     assert "diffusion_loss" in log2 and "dmd_loss" not in log2
+
+
+@pytest.mark.parametrize("maker,kw", [("LightningDiT_Mini_1", {}), ("LightningDiT_B_1", {}), ("LightningDiT_Mini_1", {"wo_shift": True})])
+def test_lightningdit_fused_glue_matches_stock_path(maker, kw):
+    """N1: under no_grad + autocast(bf16) (the DMD loss' scoring passes, train_dmd.py:212-217) LightningDiT runs RMSNorm + adaLN
+    modulate and QK-norm + RoPE as library kernels (csrc/dit_ops.cu); with grad mode on the same weights go through the
+    stock-PyTorch restatement that tests/test_dit_cpu.py pins to the real reference.  Both are bf16 pipelines with the same rounding
+    points: 1e-2 on the velocity (a handful of bf16 flips through 6 / 12 blocks)."""
+    from dmvae_b200 import dit
+    torch.manual_seed(2)
+    m = getattr(dit, maker)(input_size=16, in_channels=32, num_classes=1000, **kw)
+    for blk in m.blocks:                                  # adaLN is zero-initialised: give every modulation branch real values
+        torch.nn.init.normal_(blk.adaLN_modulation[-1].weight, std=0.02)
+        torch.nn.init.normal_(blk.attn.q_norm.weight, mean=1.0, std=0.1)
+        torch.nn.init.normal_(blk.attn.k_norm.weight, mean=1.0, std=0.1)
+        torch.nn.init.normal_(blk.norm1.weight, mean=1.0, std=0.1)
+    for lin in (m.final_layer.linear, m.final_layer.adaLN_modulation[-1]):
+        torch.nn.init.normal_(lin.weight, std=0.02)
+    m = m.to(DEV).eval()
+    x = torch.randn(3, 32, 16, 16, device=DEV)
+    t = torch.rand(3, device=DEV)
+    y = torch.randint(0, 1000, (3,), device=DEV)
+    from dmvae_b200 import _lib
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        _lib.Stats.reset()
+        with torch.no_grad():
+            fused = m(x, t, y)
+            fc, fu = m.forward_cond_uncond(x, t, y)
+        n_fused = _lib.Stats.launches
+        stock = m(x, t, y)                                # grad mode on -> ATen ops
+    assert n_fused == 2 * (3 * len(m.blocks) + 1), n_fused      # per pass: 2 modulates + 1 qk kernel per block, 1 final modulate
+    assert rel(fused.float(), stock.float().detach()) < 1e-2
+    assert rel(fc.float(), stock.float().detach()) < 1e-2
+    assert torch.isfinite(fu.float()).all()
 
 
 def test_frozen_encoder_fused_glue_matches_stock_path():
