@@ -22,6 +22,7 @@ control arm (scripts/loss_parity.py); `cpu_baseline` is the oracle step timed on
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -301,7 +302,9 @@ def measure_dmd_stage(dev, world, rank, B, cycles=2):
            "cuda_graph": tr.tr.graphed, "exchange": tr.tr.exchange_mode, "per_gpu_batch": B,
            "library_launches_per_5_iterations": lib_launches_per_cycle,
            "exchange_bytes_per_vae_turn": 4 * tr.tr.arena_vae.flat.numel(), "exchange_bytes_per_student_step": 4 * tr.tr.arena_sit.flat.numel()}
+    tr.tr.release_graphs()                         # captured NCCL operations must not outlive this leg (see shutdown_distributed)
     del tr
+    gc.collect()
     torch.cuda.empty_cache()
     return out
 
@@ -380,6 +383,7 @@ def measure_gpu_baseline(dev, B, steps=5, warmup=3):
 def run_ours(args):
     import torch.distributed as dist
     from dmvae_b200 import _lib
+    from dmvae_b200.train import shutdown_distributed
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -473,7 +477,11 @@ def run_ours(args):
                            for i, (n, t, w) in enumerate(dump)], f)
     step_ms_prof = prof_total_ms          # whole profiled step on the device (library kernels + the PyTorch ones)
     lib_ms = sum(v[1] for v in per.values())
+    release = getattr(tr, "release_graphs", None) or getattr(getattr(tr, "tr", None), "release_graphs", None)
+    if release is not None:
+        release()                         # captured NCCL operations must not outlive the trainer (see shutdown_distributed)
     del tr
+    gc.collect()
     torch.cuda.empty_cache()
 
     # secondary legs (every rank takes part in the ones that exchange)
@@ -489,9 +497,7 @@ def run_ours(args):
             extra["loss_parity"] = lp_out
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        shutdown_distributed()
         return
     peaks = load_peaks()
     tc = per.get("dmvae_conv_tc_fwd", [0, 0.0, 0.0])
@@ -531,9 +537,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_step_baseline(sample_images=1, reps=1)
     emit(out)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    shutdown_distributed()
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)

@@ -216,6 +216,45 @@ class _GraphedSection:
         self.graph.replay()
         return dict(self.out)
 
+    def release(self) -> None:
+        """Destroy the graph (and with it the captured NCCL operations).  Must happen before the process group goes away."""
+        self.graph = None
+        self.out = {}
+
+
+def shutdown_distributed(*trainers, timeout_s: float = 30.0) -> None:
+    """Orderly end of a multi-rank run: release every captured CUDA graph FIRST (a graph that holds captured NCCL collectives
+    keeps the communicator busy: destroying the process group while such graphs are alive dead-locks against ProcessGroupNCCL's
+    watchdog), drain the device, then destroy the process group -- under a watchdog of our own, because a hang at exit would
+    otherwise cost the NCCL timeout (10 minutes) on every rank."""
+    import gc
+    import os
+    import threading
+    import torch.distributed as tdist
+    for tr in trainers:
+        if tr is not None and hasattr(tr, "release_graphs"):
+            tr.release_graphs()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if not (tdist.is_available() and tdist.is_initialized()):
+        return
+
+    def _bail():
+        import sys
+        sys.stderr.write("[dmvae_b200] process-group teardown did not finish in time; exiting without it\n")
+        sys.stderr.flush()
+        os._exit(0)
+    timer = threading.Timer(timeout_s, _bail)
+    timer.daemon = True
+    timer.start()
+    try:
+        tdist.barrier()
+        torch.cuda.synchronize()
+        tdist.destroy_process_group()
+    finally:
+        timer.cancel()
+
 
 def _capture_with_exchange(fn: Callable[[], Dict[str, torch.Tensor]], arenas: List[GradArena], params: List[nn.Parameter],
                            warmup: int, optimizers: Tuple = ()) -> Tuple[_GraphedSection, str]:
@@ -345,6 +384,14 @@ class TokenizerTrainer:
     @property
     def graphed(self) -> bool:
         return self._section is not None
+
+    def release_graphs(self) -> None:
+        if self._section is not None:
+            self._section.release()
+        self._section = None
+        self._exchange_outside = True
+        self.exchange_mode = "eager"
+        self.arena.hooks_enabled = True
 
     def weights_changed(self) -> None:
         """Call after writing the trainable weights out of band (``load_state_dict``, ``load_pretrained``, manual edits) once the
@@ -494,6 +541,14 @@ class DmdTrainer:
     @property
     def graphed(self) -> bool:
         return self._sections is not None
+
+    def release_graphs(self) -> None:
+        for sec in (self._sections or {}).values():
+            sec.release()
+        self._sections = None
+        self.exchange_mode = "eager"
+        for a in (self.arena_vae, self.arena_sit):
+            a.hooks_enabled = True
 
     def step(self, images: torch.Tensor, labels: torch.Tensor, vae_turn: bool = True) -> Dict[str, torch.Tensor]:
         log: Dict[str, torch.Tensor] = {}

@@ -78,8 +78,9 @@ def main():
         assert sp_eager == 0.0, "ranks diverged: some parameter was reduced before its gradient was complete"
         assert max(errs) < 5e-3, "a replayed step stepped on a gradient that is not the cross-rank mean"
         assert sp_graph == 0.0, "ranks diverged under CUDA-graph replay"
-        print("DDP SYNC OK")
-    dist.destroy_process_group()
+        print("DDP SYNC OK", flush=True)
+    from dmvae_b200.train import shutdown_distributed
+    shutdown_distributed(tr)
 
 
 if __name__ == "__main__":

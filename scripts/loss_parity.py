@@ -147,13 +147,16 @@ def run_parity(dev, steps=100, global_batch=16, size="large", cuda_graph=True, m
                     losses[name].append(arms[arm_key].step(xg).item())
                     secs[name] += time.perf_counter() - t0
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    graph_state = (tr_forced.graphed, tr_forced.exchange_mode)
+    for _, tr in trainers.values():
+        tr.release_graphs()                        # captured NCCL operations must not outlive this run
     if world > 1:
         dist.barrier()
     if rank != 0:
         return None
     a = losses["anchor"]
     out = {"steps": steps, "global_batch": global_batch, "world": world, "per_rank_batch": B, "encoder": f"ViT-{size} (frozen)",
-           "trainer": f"TokenizerTrainer, cuda_graph={tr_forced.graphed}, exchange={tr_forced.exchange_mode}, fused clip+AdamW+EMA, lr={lr}",
+           "trainer": f"TokenizerTrainer, cuda_graph={graph_state[0]}, exchange={graph_state[1]}, fused clip+AdamW+EMA, lr={lr}",
            "tolerance_north_star": 1e-3,
            "same_weights_per_step": {
                "what": "every step, ours and the cuDNN-autocast control start from the fp32 anchor's weights: loss of identical weights "
@@ -197,9 +200,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     out = run_parity(dev, a.steps, a.global_batch, a.size, not a.no_graph, a.micro, free_running=not a.no_free)
     if out is not None:
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+        print(json.dumps(out), flush=True)
+    from dmvae_b200.train import shutdown_distributed
+    shutdown_distributed()
 
 
 if __name__ == "__main__":
