@@ -40,10 +40,9 @@ def _chk_nhwc(x: torch.Tensor, name: str) -> torch.Tensor:
 class WeightPack:
     """bf16 GEMM operands derived from one fp32 conv weight (Cout, Cin, KH, KW)."""
 
-    __slots__ = ("version", "data_ptr", "w_fwd", "w_dgrad", "_thin_wm")
+    __slots__ = ("version", "data_ptr", "w_fwd", "w_dgrad")
 
     def __init__(self):
-        self._thin_wm = None
         self.version = -1
         self.data_ptr = 0
         self.w_fwd = None
@@ -460,23 +459,8 @@ class ConvReluFn(torch.autograd.Function):
         x = _chk_nhwc(x, "conv_relu")
         cout, cin, kh, kw = weight.shape
         w_fwd, w_dgrad = pack.get(weight)
-        B, H, W, _ = x.shape
-        if (cin < 8 and kh * kw * cin <= 32 and (kh, kw) == (3, 3)
-                and query("dmvae_conv_tc_supported", B, H, W, 32, cout, 1, 1)):
-            # thin input (VGG16's 3 -> 64 stem): gather the 27 inputs of every pixel into one 64-byte row and run the conv as a 1x1 GEMM
-            # (K = 32) on the tensor-core tiles -- the CUDA-core kernel for this layer is instruction-issue bound (0.27 ms at 16 x 256^2
-            # for 134 MB of output).  Patch column j = tap' * Cin + c holds x[p - (tap' - centre)][c], i.e. the flipped tap.
-            P = torch.empty((B, H, W, 32), dtype=torch.bfloat16, device=x.device)
-            call("dmvae_grad_patches", ptr(x), ptr(P), B, H, W, cin, kh, kw, 1, 1)
-            wm = getattr(pack, "_thin_wm", None)
-            if wm is None or wm[0] != pack.version:
-                m = torch.zeros((1, cout, 32), dtype=torch.bfloat16, device=x.device)
-                m[0, :, :kh * kw * cin] = weight.detach().flip(2, 3).permute(0, 2, 3, 1).reshape(cout, kh * kw * cin).to(torch.bfloat16)
-                wm = pack._thin_wm = (pack.version, m)
-            y = conv_forward_raw(P, wm[1], None if bias is None else bias.detach(), None, 1, 1, 1, (0, 0), flags=EPI_RELU)
-        else:
-            y = conv_forward_raw(x, w_fwd, None if bias is None else bias.detach(), None, kh, kw, 1, ((kh - 1) // 2, (kw - 1) // 2),
-                                 flags=EPI_RELU)
+        y = conv_forward_raw(x, w_fwd, None if bias is None else bias.detach(), None, kh, kw, 1, ((kh - 1) // 2, (kw - 1) // 2),
+                             flags=EPI_RELU)
         ctx.geom = (kh, kw, x.shape[1:3])
         ctx.save_for_backward(x if x_is_relu else None, None if dy_premasked else y, w_fwd, w_dgrad)
         return y
