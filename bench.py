@@ -499,16 +499,16 @@ def run_ours(args):
         _lib.Stats.work_fn = _work
         _lib.Stats.timing = True
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sec_attr = "_section" if hasattr(tr, "_section") else "section"
-        saved = getattr(tr, sec_attr, None)
-        if graphed:
-            setattr(tr, sec_attr, None)
+        sec_attrs = [a for a in ("_section", "_sec_enc", "_sec_dec", "section") if hasattr(tr, a)]
+        saved = {a: getattr(tr, a) for a in sec_attrs}
+        for a in sec_attrs:
+            setattr(tr, a, None)
         pe0.record()
         tr.step(resident[0])
         pe1.record()
         torch.cuda.synchronize()
-        if graphed:
-            setattr(tr, sec_attr, saved)
+        for a in sec_attrs:
+            setattr(tr, a, saved[a])
         _lib.Stats.timing = False
         prof_total_ms = pe0.elapsed_time(pe1)
         for name, a, b, work in _lib.Stats.events:

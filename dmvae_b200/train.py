@@ -306,10 +306,20 @@ class TokenizerTrainer:
     """One VAE-pretrain step of train_tokenizer.py:403-437 (frozen encoder, recon losses, clip, AdamW, EMA).  When the loss
     function carries a discriminator (``loss_fn.disc``, BASELINE configs[3]) the step is the full GAN iteration: generator branch
     with the adaptive weight (:179-199), then the discriminator's hinge step on (images, recon.detach()) (:420-428) with its own
-    arena / fused optimizer -- the discriminator itself is whatever stock-PyTorch module the caller hands in."""
+    arena / fused optimizer -- the discriminator itself is whatever stock-PyTorch module the caller hands in.
+
+    **Pipelined exchange** (``pipelined=True``; the default with several ranks and no discriminator).  The encoder is frozen in
+    this stage (train_tokenizer.py:295-297), so its forward pass does not depend on the optimizer update.  ``step(k)`` therefore
+    runs  [all-reduce of step k-1's gradients on NCCL's stream  ||  encoder forward of batch k]  ->  clip + AdamW + EMA with
+    those gradients  ->  bottleneck + decoder forward, losses, backward of batch k -- the same arithmetic in the same order as the
+    sequential loop (the update still precedes the first use of the updated weights), but the exchange hides under the ViT's
+    library GEMMs, which tolerate the SMs NCCL takes, instead of under the persistent one-CTA-per-SM conv kernels, which do not
+    (a 148-CTA persistent grid that finds a few SMs busy finishes late by up to one NCCL kernel: measured +1.0 ms per step at 4
+    GPUs with the exchange overlapped with backward).  The update of the LAST step is applied by ``flush()`` (called by
+    ``weights_changed`` / ``release_graphs`` and to be called before reading weights, e.g. for a checkpoint)."""
 
     def __init__(self, vae: nn.Module, loss_fn: VAELossFunction, lr: float = 1e-4, wd: float = 0.0, ema: bool = True,
-                 clip: float = 1.0, lr_disc: float = 1e-4):
+                 clip: float = 1.0, lr_disc: float = 1e-4, pipelined: Optional[bool] = None):
         from .optim import FlatAdamWEMA
         self.vae = vae
         self.loss_fn = loss_fn
@@ -331,6 +341,38 @@ class TokenizerTrainer:
         self._section: Optional[_GraphedSection] = None
         self._exchange_outside = True       # eager: _forward_backward ends with the exchange itself
         self.exchange_mode = "eager"
+        if pipelined is None:
+            pipelined = GradArena._distributed() and self.arena_disc is None
+        self.pipelined = bool(pipelined) and self.arena_disc is None
+        self._pending = False               # pipelined mode: the previous step's gradients are in the arena, not yet applied
+        self._sec_enc: Optional[_GraphedSection] = None
+        self._sec_dec: Optional[_GraphedSection] = None
+        if self.pipelined:
+            self.arena.hooks_enabled = False            # the exchange is issued at the start of the NEXT step, never from backward
+            self.exchange_mode = "pipelined (eager)"
+
+    # ---- pipelined mode: the step in two pieces
+    def _encode(self, images: torch.Tensor) -> torch.Tensor:
+        with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16), torch.no_grad():
+            return self.vae.encoder(images)             # models/vae.py:92-93 with freeze_encoder=True
+
+    def _decode_backward(self, images: torch.Tensor, tokens: torch.Tensor) -> Dict[str, torch.Tensor]:
+        self.arena.zero()
+        with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
+            recon = self.vae.decoder(self.vae.bottle_neck(tokens)).float()      # models/vae.py:94-97
+            loss, log = self.loss_fn.forward_generator(images, recon, step=self.global_step)
+        with self.arena.direct():
+            loss.backward()
+        log["loss"] = loss.detach()
+        return log
+
+    def flush(self) -> Optional[torch.Tensor]:
+        """Pipelined mode: exchange and apply the gradients of the last ``step()`` now.  Returns their (pre-clip) norm."""
+        if not self._pending:
+            return None
+        self.arena.allreduce()
+        self._pending = False
+        return self.fused.step()
 
     def _forward_backward(self, images: torch.Tensor, exchange: bool = True) -> Dict[str, torch.Tensor]:
         self.arena.zero()
@@ -360,6 +402,27 @@ class TokenizerTrainer:
         backward in every replay); ``exchange_mode`` says whether that worked ("in-graph") or the exchange runs after each
         replay ("post-replay").  ``strict``: raise GraphCaptureError instead of returning False when capture fails."""
         self._section = None
+        if self.pipelined:
+            try:                                    # two graphs; the NCCL exchange stays an eager launch between them
+                self.flush()
+                self._gx = example_images.clone()
+                self._gtok = self._encode(self._gx).clone()
+
+                def enc():
+                    self._gtok.copy_(self._encode(self._gx))
+                    return {}
+                self._sec_enc = _GraphedSection(enc, [], warmup)
+                self._sec_dec = _GraphedSection(lambda: self._decode_backward(self._gx, self._gtok), self.params, warmup, (self.fused,))
+                self.exchange_mode = "pipelined under the next step's encoder forward"
+                return True
+            except Exception as e:                  # noqa: BLE001
+                self._sec_enc = self._sec_dec = None
+                torch.cuda.synchronize()
+                if strict:
+                    raise GraphCaptureError(f"TokenizerTrainer: CUDA graph capture failed ({type(e).__name__}: {e})") from e
+                import warnings
+                warnings.warn(f"TokenizerTrainer: CUDA graph capture failed ({type(e).__name__}: {e}); staying eager")
+                return False
         self.arena.hooks_enabled = True
         try:
             self._gx = example_images.clone()
@@ -383,24 +446,52 @@ class TokenizerTrainer:
 
     @property
     def graphed(self) -> bool:
-        return self._section is not None
+        return self._section is not None or self._sec_dec is not None
 
     def release_graphs(self) -> None:
-        if self._section is not None:
-            self._section.release()
-        self._section = None
+        self.flush()
+        for sec in (self._section, self._sec_enc, self._sec_dec):
+            if sec is not None:
+                sec.release()
+        self._section = self._sec_enc = self._sec_dec = None
         self._exchange_outside = True
-        self.exchange_mode = "eager"
-        self.arena.hooks_enabled = True
+        self.exchange_mode = "pipelined (eager)" if self.pipelined else "eager"
+        self.arena.hooks_enabled = not self.pipelined
 
     def weights_changed(self) -> None:
         """Call after writing the trainable weights out of band (``load_state_dict``, ``load_pretrained``, manual edits) once the
         trainer exists: bumps the version counters and rebuilds the optimizer-maintained bf16 operand copies that a captured CUDA
-        graph reads directly (an eager step would notice the stale version stamp by itself; a replayed graph cannot)."""
+        graph reads directly (an eager step would notice the stale version stamp by itself; a replayed graph cannot).  In pipelined
+        mode call ``flush()`` BEFORE overwriting the weights: a still-pending update is dropped here, not applied on top of them."""
+        if self._pending:
+            self.arena.begin_step()
+            self._pending = False
         torch.autograd.graph.increment_version(self.params)
         self.fused.sync_w16()
 
+    def _step_pipelined(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+        graphed = self._sec_dec is not None and images.shape == self._gx.shape
+        if self._pending:
+            self.arena.launch_all()                 # step k-1's gradients: on NCCL's stream, behind the backward already queued
+        if graphed:
+            self._gx.copy_(images, non_blocking=True)
+            self._sec_enc.replay()                  # ... concurrently with this batch's (frozen) encoder forward
+        else:
+            tokens = self._encode(images)
+        norm = None
+        if self._pending:
+            self.arena.finish()
+            norm = self.fused.step()                # clip + AdamW + EMA with step k-1's exchanged gradients
+        log = self._sec_dec.replay() if graphed else self._decode_backward(images, tokens)
+        if norm is not None:
+            log["vae_norm"] = norm                  # of the update applied at the start of this call (step k-1's gradients)
+        self._pending = True
+        self.global_step += 1
+        return log
+
     def step(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+        if self.pipelined:
+            return self._step_pipelined(images)
         if self._section is not None and images.shape == self._gx.shape:
             self._gx.copy_(images, non_blocking=True)
             log = self._section.replay()

@@ -141,15 +141,26 @@ class GradArena:
         if self._pending[c] == 0 and not self._launched[c]:
             self._launch(c)
 
-    def allreduce(self):
-        """Finish the exchange: launch whatever was not launched from hooks, wait, average, reset for the next step."""
+    def launch_all(self):
+        """Issue (asynchronously, on the backend's own stream, ordered after everything already queued on the current stream)
+        every chunk's all-reduce that has not been launched from a hook.  ``finish()`` completes the exchange."""
         if not self._distributed():
             return
         for c in range(len(self.bounds)):
             if not self._launched[c]:
                 self._launch(c)
+
+    def finish(self):
+        """Make the current stream wait for the launched all-reduces, average (non-NCCL backends), reset for the next step."""
+        if not self._distributed():
+            return
         for h in self._handles:
             h.wait()
         if tdist.get_backend() != "nccl":
             self.flat.div_(tdist.get_world_size())
         self.begin_step()
+
+    def allreduce(self):
+        """Finish the exchange: launch whatever was not launched from hooks, wait, average, reset for the next step."""
+        self.launch_all()
+        self.finish()

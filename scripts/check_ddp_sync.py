@@ -45,7 +45,7 @@ def main():
     g = torch.Generator().manual_seed(1000 + rank)
     xs = [(torch.rand(4, 3, 256, 256, generator=g) * 2 - 1).to(dev) for _ in range(4)]
 
-    # ---- eager path
+    # ---- eager path: the exchange finished by allreduce() equals the explicit mean
     ref = local_mean_gradient(tr, xs[0], world)
     n0 = tr.arena.exchanges
     tr._forward_backward(xs[0])
@@ -53,6 +53,7 @@ def main():
     assert tr.arena.exchanges - n0 == len(tr.arena.bounds)
     for x in xs[:3]:
         tr.step(x)
+    tr.flush()
     sp_eager = spread(tr)
 
     # ---- CUDA-graph replay
@@ -61,14 +62,23 @@ def main():
     errs = []
     for it in range(4):
         ref = local_mean_gradient(tr, xs[it], world)             # same weights on every rank (spread is 0), this step's batch
-        tr._gx.copy_(xs[it])
-        tr._section.replay()
-        if tr._exchange_outside:
-            tr.arena.allreduce()
-        errs.append(((tr.arena.flat - ref).norm() / ref.norm()).item())
-        tr.fused.step()                                          # steps on the replayed (exchanged) gradient
+        if tr.pipelined:
+            tr.step(xs[it])                                      # local gradients of this batch are in the arena, update pending
+            tr.arena.launch_all()                                # what the next step() / flush() does first
+            tr.arena.finish()
+            errs.append(((tr.arena.flat - ref).norm() / ref.norm()).item())
+            tr._pending = False
+            tr.fused.step()                                      # steps on the exchanged gradient
+        else:
+            tr._gx.copy_(xs[it])
+            tr._section.replay()
+            if tr._exchange_outside:
+                tr.arena.allreduce()
+            errs.append(((tr.arena.flat - ref).norm() / ref.norm()).item())
+            tr.fused.step()                                      # steps on the replayed (exchanged) gradient
     for x in xs:                                                 # and the public step()
         tr.step(x)
+    tr.flush()
     sp_graph = spread(tr)
     if rank == 0:
         print(f"world {world}: eager exchanged-vs-explicit mean gradient rel err {err_eager:.3e}; parameter spread after 3 eager steps {sp_eager:.3e}")

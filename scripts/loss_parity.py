@@ -64,6 +64,7 @@ def _force_weights(tr, vae, arm, world):
     """Teacher forcing: overwrite the trainer's trainable weights with the stock arm's current ones (rank 0 holds the arm; the
     other ranks receive them by broadcast)."""
     import torch.distributed as dist
+    tr.flush()                                     # pipelined trainer: apply the pending update BEFORE the weights are overwritten
     if arm is not None:
         src = dict(("decoder." + k, v) for k, v in arm.sd.items())
         src.update(("bottle_neck." + k, v) for k, v in arm.mlp.state_dict().items())

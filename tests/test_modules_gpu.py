@@ -647,6 +647,40 @@ def test_tokenizer_trainer_cuda_graph_matches_eager():
     assert rel(pg, pe) < 1e-2
 
 
+def test_tokenizer_trainer_pipelined_exchange_is_the_same_training():
+    """TokenizerTrainer(pipelined=True) -- exchange + update of step k-1 issued at the start of step k, next to the frozen encoder's
+    forward -- must train exactly like the sequential trainer: same per-step losses (same arithmetic in the same order; bf16
+    run-to-run noise only), same weights after flush(); eagerly and with its two CUDA graphs."""
+    from dmvae_b200.vae import VAE
+    from dmvae_b200.lpips import LPIPS
+    from dmvae_b200.train import LossConfig, TokenizerTrainer, VAELossFunction
+
+    def make(pipelined):
+        torch.manual_seed(0)
+        vae = VAE(z_channels=32, model_size="base").to(DEV)
+        vae.encoder.eval()
+        for p in vae.encoder.parameters():
+            p.requires_grad = False
+        lp = LPIPS(ckpt_path=None, pretrained_vgg=False).eval().to(DEV)
+        return TokenizerTrainer(vae, VAELossFunction(LossConfig(), lpips_loss=lp), lr=2e-4, pipelined=pipelined)
+
+    g = torch.Generator(device=DEV).manual_seed(5)
+    batches = [torch.rand(2, 3, 256, 256, device=DEV, generator=g) * 2 - 1 for _ in range(5)]
+    seq, pipe, pipe_g = make(False), make(True), make(True)
+    assert pipe.pipelined and not seq.pipelined
+    assert pipe_g.capture_cuda_graph(batches[0], strict=True)
+    for i, x in enumerate(batches):
+        a, b, c = seq.step(x), pipe.step(x), pipe_g.step(x)
+        for other in (b, c):
+            assert abs(a["loss"].item() - other["loss"].item()) <= 1e-2 * abs(a["loss"].item()), i
+        assert ("vae_norm" in b) == (i > 0)                      # the first call has no previous gradients to apply
+    assert pipe.flush() is not None and pipe.flush() is None
+    pipe_g.flush()
+    ws = torch.cat([p.detach().reshape(-1) for p in seq.params])
+    for tr in (pipe, pipe_g):
+        assert rel(torch.cat([p.detach().reshape(-1) for p in tr.params]), ws) < 1e-2
+
+
 def test_decoder_production_size_against_reference_outputs():
     """The production decoder on the GPU (bf16 pipeline, every layer on its production kernel, fwd + bwd) against what the REAL
     reference module (fp32, CPU) produced for the same weights and tokens: tests/golden/decoder_full.pt (make_golden_full.py).
