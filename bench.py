@@ -494,6 +494,7 @@ def run_ours(args):
 
     # one profiled step: CUDA events around every library launch (issued eagerly so that every launch can be bracketed)
     per, dump, prof_total_ms = {}, [], 0.0
+    per_kernel = {}
     if args.workload != "dmd" or not graphed:
         _lib.Stats.reset()
         _lib.Stats.work_fn = _work
@@ -511,11 +512,15 @@ def run_ours(args):
             setattr(tr, a, saved[a])
         _lib.Stats.timing = False
         prof_total_ms = pe0.elapsed_time(pe1)
-        for name, a, b, work in _lib.Stats.events:
+        for i, (name, a, b, work) in enumerate(_lib.Stats.events):
             d = per.setdefault(name, [0, 0.0, 0.0])
             t = a.elapsed_time(b)
             d[0] += 1; d[1] += t; d[2] += work
             dump.append((name, t, work))
+            kid = _lib.Stats.kernel_ids[i] if i < len(_lib.Stats.kernel_ids) else 0
+            if kid and "wgrad" not in name:                     # forward / data-gradient launches by the tile kernel that ran them
+                k = per_kernel.setdefault(kid, [0, 0.0, 0.0])
+                k[0] += 1; k[1] += t; k[2] += work
         if os.environ.get("BENCH_DUMP_LAUNCHES") and rank == 0:     # per-launch (entry point, ms, algorithmic flops) of the profiled step
             with open(os.environ["BENCH_DUMP_LAUNCHES"], "w") as f:
                 json.dump([{"name": n, "ms": round(t, 4), "work": w, "args": list(_lib.Stats.args_log[i]) if i < len(_lib.Stats.args_log) else None}
@@ -549,17 +554,32 @@ def run_ours(args):
     for name in ("dmvae_conv_tc_fwd", "dmvae_conv_up2x_fwd", "dmvae_conv_up2x_dgrad"):
         v = per.get(name, [0, 0.0, 0.0])
         tc = [tc[0] + v[0], tc[1] + v[1], tc[2] + v[2]]
-    achieved = tc[2] / (tc[1] * 1e-3) / 1e12 if tc[1] > 0 else 0.0
     step_ms = ms / args.steps
-    roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv tiles (conv_tc2h / conv_tcT / conv_tc2 / conv_tc kernels: all forward + "
-                                          "data-gradient launches of a step, sub-pixel Upsample counted at its EXECUTED flops)",
-            "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-            "frac": round(achieved / peaks["tf_sustained"], 4), "peak_source": f"{peaks['src']} (sustained: kernel timed inside a long step)",
-            "frac_of_burst_peak": round(achieved / peaks["tf_burst"], 4), "burst_peak": peaks["tf_burst"],
-            "launches_per_step": tc[0], "avg_launch_ms": round(tc[1] / max(tc[0], 1), 4),
-            "flops_per_launch_avg": tc[2] / max(tc[0], 1), "traffic": None,
-            "share_of_step": round(tc[1] / max(step_ms, 1e-9), 4),
-            "share_note": "sum of these launches' CUDA-event durations (taken in one eagerly issued step) / the timed step"}
+    knames = {1: "conv_tc_kernel (single-CTA per-tap tile)", 2: "conv_tc2_kernel (per-tap CTA pair: 1x1 / stride-2 / small images)",
+              3: "conv_tc2h_kernel (halo-resident CTA-pair tile, cta_group::2 UMMA 256x256x16; plain 3x3 and sub-pixel Upsample launches)",
+              4: "conv_tcT_kernel (transposed tile for 64 / 128 / thin outputs)"}
+
+    def roof_entry(v, kernel):
+        ach = v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0
+        return {"bound": "tensor", "kernel": kernel, "achieved": round(ach, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / peaks["tf_sustained"], 4),
+                "peak_source": f"{peaks['src']} (sustained: kernel timed inside a long step)",
+                "frac_of_burst_peak": round(ach / peaks["tf_burst"], 4), "burst_peak": peaks["tf_burst"],
+                "launches_per_step": v[0], "avg_launch_ms": round(v[1] / max(v[0], 1), 4),
+                "flops_per_launch_avg": v[2] / max(v[0], 1), "traffic": None,
+                "share_of_step": round(v[1] / max(step_ms, 1e-9), 4),
+                "share_note": "sum of these launches' CUDA-event durations (taken in one eagerly issued step) / the timed step; "
+                              "sub-pixel Upsample launches counted at their EXECUTED flops"}
+    # the dominant kernel of the step = the tile kernel with the largest summed duration (attributed per launch by the library's
+    # dmvae_conv_tc_last_kernel hook); the aggregate over every forward + data-gradient conv launch is kept beside it
+    roof_all = roof_entry(tc, "all tcgen05 conv tiles: every forward + data-gradient launch of a step (conv_tc2h / conv_tcT / conv_tc2 / conv_tc)")
+    if per_kernel:
+        dom = max(per_kernel, key=lambda k: per_kernel[k][1])
+        roof = roof_entry(per_kernel[dom], knames.get(dom, f"kernel id {dom}") + ": all its forward + data-gradient launches of a step")
+        roof["by_kernel"] = {knames.get(k, str(k)).split(" ")[0]: {"n": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1) if v[1] else None}
+                             for k, v in sorted(per_kernel.items())}
+    else:
+        roof = roof_all
     wg = [0, 0.0, 0.0]
     for name in ("dmvae_conv_tc_wgrad", "dmvae_conv_up2x_wgrad"):
         v = per.get(name, [0, 0.0, 0.0])
@@ -577,6 +597,7 @@ def run_ours(args):
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": B * 3 * res * res * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last.get("loss")},
         "gpu_launches": launches, "host_issue_ms_per_step": round(host_issue_ms, 3), "clocks": clocks, "roofline": roof,
+        "roofline_all_conv_tiles": roof_all,
         "wgrad": {"achieved_tflops": round(wg[2] / (wg[1] * 1e-3) / 1e12, 1) if wg[1] else None, "launches_per_step": wg[0],
                   "share_of_step": round(wg[1] / max(step_ms, 1e-9), 4)},
         "profiled_step_ms": {"total": round(prof_total_ms, 3), "library_kernels": round(lib_ms, 3)},

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvae_b200.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 5          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
+ABI_VERSION = 6          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> argtypes  (every function returns int except dmvae_last_error)
@@ -38,6 +38,7 @@ SIGNATURES = {
     "dmvae_conv_tc_supported": [_i] * 7,
     "dmvae_conv_tc_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "dmvae_conv_tc_set_tile_mode": [_i],
+    "dmvae_conv_tc_last_kernel": [],
     "dmvae_conv_tc_strided_supported": [_i] * 10,
     "dmvae_conv_tc_fwd_strided": [_p, _p, _p, _p] + [_i] * 12 + [_p],
     "dmvae_conv_tc_wgrad_strided": [_p, _p, _p] + [_i] * 12 + [_p],
@@ -134,6 +135,7 @@ class Stats:
     timing = False
     events = []          # (name, start_event, end_event, work) ; work = algorithmic flops or bytes, see bench.py
     args_log = []        # integer arguments of each timed call (shapes), parallel to ``events``
+    kernel_ids = []      # dmvae_conv_tc_last_kernel() after each timed conv call (0 otherwise), parallel to ``events``
     work_fn = None       # callable(name, args) -> float
 
     @classmethod
@@ -141,6 +143,7 @@ class Stats:
         cls.launches = 0
         cls.events = []
         cls.args_log = []
+        cls.kernel_ids = []
 
 
 def call(name: str, *args) -> None:
@@ -160,6 +163,7 @@ def call(name: str, *args) -> None:
         rc = getattr(lib, name)(*args, _stream())
         e1.record()
         Stats.events.append((name, e0, e1, Stats.work_fn(name, args) if Stats.work_fn else 0.0))
+        Stats.kernel_ids.append(lib.dmvae_conv_tc_last_kernel() if name.startswith(("dmvae_conv_tc", "dmvae_conv_up2x")) else 0)
         Stats.args_log.append(tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 20)))
     else:
         rc = getattr(lib, name)(*args, _stream())

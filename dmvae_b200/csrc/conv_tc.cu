@@ -33,6 +33,10 @@
 
 namespace {
 
+// kernel ids reported by dmvae_conv_tc_last_kernel (include/dmvae_b200.h)
+constexpr int DMVAE_KERNEL_CONV_TC = 1, DMVAE_KERNEL_CONV_TC2 = 2, DMVAE_KERNEL_CONV_TC2H = 3, DMVAE_KERNEL_CONV_TCT = 4,
+              DMVAE_KERNEL_WGRAD = 5, DMVAE_KERNEL_WGRAD2 = 6;
+
 constexpr int BM = 128;        // pixels per tile (UMMA M)
 constexpr int BK = 64;         // channels per pipeline stage (one 128-byte swizzle row)
 constexpr int UMMA_K = 16;
@@ -1623,6 +1627,8 @@ int pick_pixel_tile_n(int H, int W, int pixels, int* BW, int* BH) {
 int pick_pixel_tile(int H, int W, int* BW, int* BH) { return pick_pixel_tile_n(H, W, BM, BW, BH); }
 
 int pick_pixel_tile64(int H, int W, int* BW, int* BH);
+// which kernel the last conv entry point called on this thread launched (dmvae_conv_tc_last_kernel: measurement hook)
+thread_local int g_last_kernel = 0;
 int g_num_sms = 0;
 int num_sms() {
     if (!g_num_sms) {
@@ -1656,6 +1662,7 @@ int launch_conv_tc(const void* x, const void* w, const float* bias, const void* 
     const int tiles = g.m_tiles * g.n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     conv_tc_kernel<BN, MT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, stats, g);
+    g_last_kernel = DMVAE_KERNEL_CONV_TC;
     DMVAE_CHECK_LAUNCH("conv_tc_kernel");
     return DMVAE_OK;
 }
@@ -1682,6 +1689,7 @@ int launch_conv_tc2(const void* x, const void* w, const float* bias, const void*
     const int pair_tiles = (g.m_tiles / 2) * g.n_tiles;
     const int clusters = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
     conv_tc2_kernel<BN><<<2 * clusters, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, stats, g);
+    g_last_kernel = DMVAE_KERNEL_CONV_TC2;
     DMVAE_CHECK_LAUNCH("conv_tc2_kernel");
     return DMVAE_OK;
 }
@@ -1707,6 +1715,7 @@ int launch_conv_tc2h(const void* x, const void* w, const float* bias, const void
     const int pair_tiles = (g.m_tiles / 2) * g.n_tiles;
     const int clusters = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
     conv_tc2h_kernel<BN><<<2 * clusters, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, (const bf16*)res, (bf16*)y, stats, g);
+    g_last_kernel = DMVAE_KERNEL_CONV_TC2H;
     DMVAE_CHECK_LAUNCH("conv_tc2h_kernel");
     return DMVAE_OK;
 }
@@ -1736,6 +1745,7 @@ int launch_conv_tc2h_up(const void* a, const void* w16, const float* bias, void*
     const int pair_tiles = (g.m_tiles / 2) * g.n_tiles * (g.up == 1 ? 4 : 1);
     const int clusters = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
     conv_tc2h_kernel<BN><<<2 * clusters, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, bias, nullptr, (bf16*)y, stats, g);
+    g_last_kernel = DMVAE_KERNEL_CONV_TC2H;
     DMVAE_CHECK_LAUNCH("conv_tc2h_kernel (sub-pixel)");
     return DMVAE_OK;
 }
@@ -1760,6 +1770,7 @@ int launch_conv_tcT(const void* x, const void* w, const float* bias, const void*
     const int tiles = g.m_tiles * g.n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     conv_tcT_kernel<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mx, mw, bias, (const bf16*)res, (bf16*)y, stats, g);
+    g_last_kernel = DMVAE_KERNEL_CONV_TCT;
     DMVAE_CHECK_LAUNCH("conv_tcT_kernel");
     return DMVAE_OK;
 }
@@ -1771,6 +1782,10 @@ int g_wgrad_tpc = 3;         // taps per CTA of the 128-channel weight-gradient 
 int g_halo = 1;              // halo-resident pair tiles for 3x3 filters (modes 6 / 7 turn it off / on)
 
 }  // namespace
+
+// Measurement hook (host only): which tile kernel the most recent tcgen05 conv entry point called on this thread launched --
+// 1 conv_tc_kernel, 2 conv_tc2_kernel, 3 conv_tc2h_kernel, 4 conv_tcT_kernel, 5 conv_tc_wgrad_kernel, 6 conv_tc_wgrad2_kernel, 0 none yet.
+DMVAE_API int dmvae_conv_tc_last_kernel(void) { return g_last_kernel; }
 
 // 1 if (shape) can run on the tcgen05 tile, else 0 (caller uses conv_direct)
 DMVAE_API int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW) {
@@ -1905,6 +1920,7 @@ int launch_wgrad_tc(const void* x, const void* dy, float* dwp, WgGeom g, cudaStr
     g.splits = (g.pix_tiles + g.tiles_per_split - 1) / g.tiles_per_split;
     dim3 grid((unsigned)base, (unsigned)g.splits);
     conv_tc_wgrad_kernel<BN, MT, TPC><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mdy, mx, dwp, g);
+    g_last_kernel = DMVAE_KERNEL_WGRAD;
     DMVAE_CHECK_LAUNCH("conv_tc_wgrad_kernel");
     return DMVAE_OK;
 }
@@ -1939,6 +1955,7 @@ int launch_wgrad_tc2(const void* x, const void* dy, float* dwp, WgGeom g, cudaSt
     g.splits = (g.pix_tiles + g.tiles_per_split - 1) / g.tiles_per_split;
     dim3 grid((unsigned)(2 * base), (unsigned)g.splits);
     conv_tc_wgrad2_kernel<MT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mdy, mx, dwp, g);
+    g_last_kernel = DMVAE_KERNEL_WGRAD2;
     DMVAE_CHECK_LAUNCH("conv_tc_wgrad2_kernel");
     return DMVAE_OK;
 }

@@ -34,7 +34,7 @@ extern "C" {
 
 /* Bumped whenever a prototype below changes; the ctypes binding (dmvae_b200/_lib.py) refuses a library whose
  * dmvae_abi_version() differs from the table it was written against. */
-#define DMVAE_ABI_VERSION 5
+#define DMVAE_ABI_VERSION 6
 
 const char* dmvae_last_error(void);
 int dmvae_abi_version(void);
@@ -175,6 +175,11 @@ int dmvae_subpixel_fold_wgrad(const float* dwp, float* dw3, int64_t stride_co, i
  * 4 / 5 = CTA pairs preferred / never; 6 / 7 = halo + transposed tiles off / on; 8 = halo + transposed tiles wherever the shape
  * allows, ignoring the occupancy thresholds (tests); 12 / 13 / 14 = taps per CTA (2 / 3 / 4) of the 128-channel weight gradient. */
 int dmvae_conv_tc_set_tile_mode(int mode);
+/* Measurement hook (host only): the tile kernel launched by the most recent tcgen05 conv entry point called on this thread:
+ * 1 conv_tc_kernel, 2 conv_tc2_kernel (per-tap pair), 3 conv_tc2h_kernel (halo pair, incl. the sub-pixel modes),
+ * 4 conv_tcT_kernel (transposed), 5 conv_tc_wgrad_kernel, 6 conv_tc_wgrad2_kernel (pair); 0 = none yet.  bench.py uses it to
+ * attribute each timed launch to its kernel. */
+int dmvae_conv_tc_last_kernel(void);
 
 /* tcgen05 weight gradient (both operands MN-major): dw_tap_major[tap][Cout][Cin] (fp32, caller-zeroed or
  * accumulated) += sum_pixels dy[p][co] * x[p(+)tap][ci].  Replaces cuDNN backward-filter for the same call sites.
