@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvae_b200.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 6          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
+ABI_VERSION = 7          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> argtypes  (every function returns int except dmvae_last_error)
@@ -67,6 +67,7 @@ SIGNATURES = {
     "dmvae_add_bf16": [_p, _p, _p, _i64, _p],
     "dmvae_scale_residual": [_p, _p, _p, _i64, _i, _p],
     "dmvae_layernorm_bf16": [_p, _p, _p, _p, _i64, _i, _f, _p],
+    "dmvae_scale_residual_layernorm": [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p],
     "dmvae_rmsnorm_modulate": [_p, _i, _p, _p, _p, _i64, _p, _i64, _i, _i, _f, _p],
     "dmvae_qk_norm_rope": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _f, _p],
     "dmvae_grad_sumsq": [_p, _p, _i64, _p],

@@ -155,6 +155,17 @@ def _scale_residual_(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor) -> t
     return x
 
 
+def _scale_residual_ln_(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, norm: nn.LayerNorm) -> torch.Tensor:
+    """x += y * gamma in place, and returns bf16 LayerNorm(x) with ``norm``'s parameters (the next branch's pre-norm): one kernel,
+    bit-identical to _scale_residual_ followed by _ln_bf16."""
+    if y.dtype != torch.bfloat16 or not y.is_contiguous():
+        return _ln_bf16(norm, _scale_residual_(x, y, gamma))
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    call("dmvae_scale_residual_layernorm", ptr(x), ptr(y), ptr(gamma), ptr(norm.weight), ptr(norm.bias), ptr(out),
+         x.numel() // x.shape[-1], x.shape[-1], float(norm.eps))
+    return out
+
+
 class _Block(nn.Module):
     def __init__(self, dim, heads):
         super().__init__()
@@ -191,6 +202,18 @@ class DinoViT(nn.Module):
     def forward_features(self, x):
         x = self.patch_embed(x)
         x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1) + self.pos_embed
+        if _fused_glue_ok(x, x.shape[-1]) and len(self.blocks) > 0:
+            # frozen pass: every LayerScale + residual update is fused with the LayerNorm that follows it (the same block's norm2, or
+            # the next block's norm1), so a block costs two glue launches instead of four; x is a fresh tensor owned by this pass
+            h = _ln_bf16(self.blocks[0].norm1, x)
+            for i, blk in enumerate(self.blocks):
+                h = _scale_residual_ln_(x, blk.attn(h), blk.ls1.gamma, blk.norm2)
+                y = blk.mlp(h)
+                if i + 1 < len(self.blocks):
+                    h = _scale_residual_ln_(x, y, blk.ls2.gamma, self.blocks[i + 1].norm1)
+                else:
+                    x = _scale_residual_(x, y, blk.ls2.gamma)
+            return self.norm(x)
         for blk in self.blocks:                     # x is a fresh tensor owned by this pass
             x = blk(x, own_buffer=True)
         return self.norm(x)

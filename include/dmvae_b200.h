@@ -34,7 +34,7 @@ extern "C" {
 
 /* Bumped whenever a prototype below changes; the ctypes binding (dmvae_b200/_lib.py) refuses a library whose
  * dmvae_abi_version() differs from the table it was written against. */
-#define DMVAE_ABI_VERSION 6
+#define DMVAE_ABI_VERSION 7
 
 const char* dmvae_last_error(void);
 int dmvae_abi_version(void);
@@ -241,6 +241,10 @@ int dmvae_relu_mask(const void* y, const void* dy, void* out, int64_t n, void* s
  *   next Linear casts its input to bf16). */
 int dmvae_scale_residual(float* x, const void* y_bf16, const float* gamma, int64_t rows, int D, void* stream);
 int dmvae_layernorm_bf16(const float* x, const float* weight, const float* bias, void* y_bf16, int64_t rows, int D, float eps, void* stream);
+/* The two above back to back in one pass (the row stays in registers): x += float(y) * gamma, then out = bf16(LayerNorm(x)) with
+ * the NEXT branch's LayerNorm parameters -- bit-identical to the two-call sequence, one launch and one read of x fewer. */
+int dmvae_scale_residual_layernorm(float* x, const void* y_bf16, const float* gamma, const float* weight, const float* bias,
+                                   void* out_bf16, int64_t rows, int D, float eps, void* stream);
 
 /* ------------------------------------------------------------------ N1: LightningDiT glue (no-grad scoring passes) ---- */
 /* The teacher / student velocity networks are evaluated without autograd four times per VAE turn (train_dmd.py:212-217); the

@@ -602,3 +602,25 @@ def test_vit_glue_layernorm_bf16(D):
     assert (d <= ref.abs() * 2 ** -7 + 1e-6).all(), d.max()
     assert (d > 0).float().mean() < 1e-3
     assert rel_err(y.float(), ref) < 3e-3            # bf16 rounding of the output itself
+
+
+@pytest.mark.parametrize("D", [384, 768, 1024])
+def test_vit_glue_scale_residual_layernorm_is_the_two_kernels_back_to_back(D):
+    """dmvae_scale_residual_layernorm = dmvae_scale_residual followed by dmvae_layernorm_bf16, bit for bit (residual stream and the
+    bf16 LayerNorm output), on an odd row count (16 x 257 tokens)."""
+    from dmvae_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(D + 1)
+    rows = 4112
+    x0 = torch.randn(rows, D, generator=g, device=DEV) * 2 + 0.3
+    y = torch.randn(rows, D, generator=g, device=DEV).bfloat16()
+    gamma = torch.randn(D, generator=g, device=DEV) * 0.2
+    w = torch.rand(D, generator=g, device=DEV) + 0.5
+    b = torch.randn(D, generator=g, device=DEV) * 0.1
+    xa, xb = x0.clone(), x0.clone()
+    oa = torch.empty(rows, D, dtype=torch.bfloat16, device=DEV)
+    ob = torch.empty_like(oa)
+    _lib.call("dmvae_scale_residual", _lib.ptr(xa), _lib.ptr(y), _lib.ptr(gamma), rows, D)
+    _lib.call("dmvae_layernorm_bf16", _lib.ptr(xa), _lib.ptr(w), _lib.ptr(b), _lib.ptr(oa), rows, D, 1e-6)
+    _lib.call("dmvae_scale_residual_layernorm", _lib.ptr(xb), _lib.ptr(y), _lib.ptr(gamma), _lib.ptr(w), _lib.ptr(b), _lib.ptr(ob), rows, D, 1e-6)
+    torch.cuda.synchronize()
+    assert torch.equal(xa, xb) and torch.equal(oa, ob)
