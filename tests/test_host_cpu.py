@@ -256,3 +256,49 @@ def test_abi_rejects_null_pointers_without_touching_the_device():
         assert name.replace("dmvae_", "").split("_fwd")[0].split("_bwd")[0][:6] in msg or "null" in msg or "pointer" in msg, (name, msg)
         checked += 1
     assert checked >= 25
+
+
+def test_grad_arena_layout_tap_major_views_and_padding():
+    """Arena layout contract (dmvae_b200/train_arena.py): every parameter starts on an 8-element boundary, 3x3 conv weights are stored
+    tap-major ([tap][Cout][Cin]) behind a strided (Cout, Cin, 3, 3) view, everything else keeps its natural order; flatten() lays
+    per-parameter tensors out the same way.  Pure host logic: runs without a GPU."""
+    from dmvae_b200.train_arena import GradArena, arena_view, tap_major
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(5, 7, 3), torch.nn.Conv2d(7, 3, 1), torch.nn.GroupNorm(1, 3), torch.nn.Linear(3, 2))
+    arena = GradArena(net.parameters())
+    assert all(off % 8 == 0 for off in arena.offsets) and arena.flat.numel() % 8 == 0
+    w3, w1 = net[0].weight, net[1].weight
+    assert tap_major(w3) and not tap_major(w1) and not tap_major(net[3].weight)
+    assert w3.grad.shape == w3.shape and w3.grad.stride() == (5, 1, 3 * 7 * 5, 7 * 5)
+    assert w1.grad.is_contiguous() and net[0].bias.grad.is_contiguous()
+    vals = [torch.randn(p.shape) for p in arena.params]
+    for p, v in zip(arena.params, vals):
+        p.grad.copy_(v)
+    flat = arena.flatten(vals)
+    assert torch.equal(flat, arena.flat)
+    off = arena.offsets[0]
+    assert torch.equal(arena.flat[off:off + w3.numel()].view(9, 7, 5), vals[0].permute(2, 3, 0, 1).reshape(9, 7, 5))
+    used = torch.zeros_like(arena.flat, dtype=torch.bool)
+    for p, off in zip(arena.params, arena.offsets):
+        used[off:off + p.numel()] = True
+    assert float(arena.flat[~used].abs().sum()) == 0.0               # padding stays zero
+    assert arena_view(arena.flat, arena.offsets[1], net[0].bias).data_ptr() == net[0].bias.grad.data_ptr()
+    # backward accumulates through the strided view like through any .grad
+    arena.zero()
+    x = torch.randn(2, 5, 6, 6)
+    ref = torch.autograd.grad(net[:3](x).square().mean(), [w3])[0]
+    net[:3](x).square().mean().backward()
+    assert torch.allclose(w3.grad, ref) and w3.grad.data_ptr() == arena.flat.data_ptr() + 4 * arena.offsets[0]
+
+
+def test_shutdown_distributed_without_process_group_is_a_noop():
+    from dmvae_b200.train import shutdown_distributed
+
+    class T:
+        released = False
+
+        def release_graphs(self):
+            self.released = True
+    t = T()
+    shutdown_distributed(t, None)
+    assert t.released
