@@ -17,7 +17,7 @@ train_dmd.py:212-217).  What this module adds over the reference:
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 import torch

@@ -5,12 +5,11 @@ host.  Call ``.item()`` yourself when you want to log, as the reference does (tr
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Tuple
 
 import torch
 
-from . import _lib
-from ._lib import BF16, F32, call, dtype_code, ptr
+from ._lib import call, dtype_code, ptr
 
 
 def _flat2(x: torch.Tensor) -> Tuple[torch.Tensor, int, int]:

@@ -17,7 +17,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, call, ptr, query
+from ._lib import call, ptr, query
 
 GN_EPS = 1e-6
 EPI_RELU, EPI_MASK = 1, 2      # conv epilogue flags (csrc/conv_tc.cu): ReLU on the output / `residual` gates the output
