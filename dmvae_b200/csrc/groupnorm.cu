@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(GN_THREADS, U <= 2 ? 3 : 2) gn_bwd_apply_kerne
     const bf16* __restrict__ da, const bf16* __restrict__ x, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ gsum,
     const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ colsum, int64_t HW, int C, int vc, int rows,
-    int64_t ppb, float eps) {
+    int64_t ppb, float eps, int reverse) {
     extern __shared__ float s_mem[];   // a[C] b[C] k0[C] k1[C]
     float* s_a = s_mem; float* s_b = s_mem + C; float* s_k0 = s_mem + 2 * C; float* s_k1 = s_mem + 3 * C;
     const int b = blockIdx.y;
@@ -262,20 +262,26 @@ __global__ void __launch_bounds__(GN_THREADS, U <= 2 ? 3 : 2) gn_bwd_apply_kerne
     const int64_t p0 = (int64_t)blockIdx.x * ppb;
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
     const int64_t off = (int64_t)b * HW * C + col * 8;
+    // This pass walks its pixel range BACKWARDS: the reduce pass (same grid, same ranges) has just streamed da and x front to back,
+    // so what is still in the 126 MB L2 is the tail of every CTA's range -- read first here, before this pass's own traffic evicts it
+    // (front-to-back after front-to-back is the LRU worst case: nothing would hit).
+    const int64_t plast = p0 + p1 - 1;
     for (int64_t p = p0 + row; p < p1; p += (int64_t)rows * U) {
         uint4 vx[U], vd[U], vr[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t pp = p + (int64_t)u * rows;
-            const bool ok = pp < p1;
+            const int64_t pl = p + (int64_t)u * rows;
+            const bool ok = pl < p1;
+            const int64_t pp = reverse ? plast - pl : pl;
             vx[u] = ok ? ld_stream16(x + off + pp * C) : make_uint4(0, 0, 0, 0);
             vd[u] = ok ? ld_stream16(da + off + pp * C) : make_uint4(0, 0, 0, 0);
             vr[u] = (ok && dres) ? ld_stream16(dres + off + pp * C) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t pp = p + (int64_t)u * rows;
-            if (pp >= p1) break;
+            const int64_t pl = p + (int64_t)u * rows;
+            if (pl >= p1) break;
+            const int64_t pp = reverse ? plast - pl : pl;
             float fx[8], fd[8], fr[8];
             unpack_bf16x8(vx[u], fx);
             unpack_bf16x8(vd[u], fd);
@@ -357,6 +363,8 @@ DMVAE_API int dmvae_gn_bwd(const void* da, const void* x, const double* stats, c
     const size_t smem = (size_t)4 * C * sizeof(float);
     const size_t smem_r = (size_t)6 * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    static int reverse = -1;         // DMVAE_GN_BWD_REVERSE=0 turns the backwards walk of the apply pass off (A/B measurements)
+    if (reverse < 0) { const char* e = getenv("DMVAE_GN_BWD_REVERSE"); reverse = e ? (atoi(e) != 0) : 1; }
     static int U = 0;
     if (!U) { const char* e = getenv("DMVAE_GN_BWD_U"); U = e ? atoi(e) : 4; if (U != 2 && U != 3 && U != 4) U = 4; }     // 16-byte loads in flight per tensor per thread
 #define GN_BWD_LAUNCH(S, UU)                                                                                                              \
@@ -365,7 +373,8 @@ DMVAE_API int dmvae_gn_bwd(const void* da, const void* x, const double* stats, c
                                                                       dbeta, HW, C, g.vc, g.rows, ppb, eps);                              \
         DMVAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");                                                                                       \
         gn_bwd_apply_kernel<S, UU><<<grid, GN_THREADS, smem, st>>>((const bf16*)da, (const bf16*)x, stats, gamma, beta, gsum,            \
-                                                                   (const bf16*)dres, (bf16*)dx, dx_colsum, HW, C, g.vc, g.rows, ppb, eps); \
+                                                                   (const bf16*)dres, (bf16*)dx, dx_colsum, HW, C, g.vc, g.rows, ppb, eps, \
+                                                                   reverse);                                                              \
     } while (0)
     if (silu) {
         if (U == 2) GN_BWD_LAUNCH(true, 2); else if (U == 3) GN_BWD_LAUNCH(true, 3); else GN_BWD_LAUNCH(true, 4);
