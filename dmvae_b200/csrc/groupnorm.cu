@@ -263,8 +263,9 @@ __global__ void __launch_bounds__(GN_THREADS, U <= 2 ? 3 : 2) gn_bwd_apply_kerne
     const int64_t p1 = (p0 + ppb < HW) ? p0 + ppb : HW;
     const int64_t off = (int64_t)b * HW * C + col * 8;
     // This pass walks its pixel range BACKWARDS: the reduce pass (same grid, same ranges) has just streamed da and x front to back,
-    // so what is still in the 126 MB L2 is the tail of every CTA's range -- read first here, before this pass's own traffic evicts it
-    // (front-to-back after front-to-back is the LRU worst case: nothing would hit).
+    // so whatever the L2 still holds is the tail of every CTA's range -- read first here, before this pass's own traffic evicts it.
+    // Measured on B200 (same-box A/B, DMVAE_GN_BWD_REVERSE=0/1): -0.05 ms per step only -- little of a 0.3-0.5 GB stream survives
+    // in the 126 MB L2 next to the write-back traffic -- kept because it is free.
     const int64_t plast = p0 + p1 - 1;
     for (int64_t p = p0 + row; p < p1; p += (int64_t)rows * U) {
         uint4 vx[U], vd[U], vr[U];
