@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvae_b200.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 7          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
+ABI_VERSION = 8          # must equal dmvae_abi_version() of the loaded library (include/dmvae_b200.h: DMVAE_ABI_VERSION)
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> argtypes  (every function returns int except dmvae_last_error)
@@ -74,6 +74,7 @@ SIGNATURES = {
     "dmvae_adamw_ema_step": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _f, _p],
     "dmvae_cast_bf16": [_p, _p, _i64, _p],
     "dmvae_pack_dgrad_bf16": [_p, _p, _i, _i, _i, _p],
+    "dmvae_pack_dgrad_batched": [_p, _p, _p, _i, _i64, _p],
 }
 
 _lib: Optional[C.CDLL] = None

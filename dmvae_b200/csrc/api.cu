@@ -13,7 +13,7 @@ int dmvae_set_error(int code, const char* fmt, ...) {
 }
 
 DMVAE_API const char* dmvae_last_error(void) { return g_err; }
-DMVAE_API int dmvae_abi_version(void) { return 7; }
+DMVAE_API int dmvae_abi_version(void) { return 8; }
 
 // Device the library was built for; lets the host side fail loudly on anything but sm_100.
 DMVAE_API int dmvae_check_device(void) {

@@ -445,6 +445,52 @@ DMVAE_API int dmvae_pack_dgrad_bf16(const void* w_fwd, void* w_dgrad, int Cout, 
     return DMVAE_OK;
 }
 
+// The same transpose for EVERY conv weight of a flat bf16 arena in one launch (the optimizer issues it right after its update
+// kernel, optim.py): desc[i] = {element offset of the parameter in both arenas, Cout, Cin, taps, index of its first 32x32 tile};
+// a CTA finds its descriptor by binary search over the tile starts.  Tiles of one parameter are ordered [tap][ci tile][co tile].
+__global__ void __launch_bounds__(256) pack_dgrad_batched_kernel(const bf16* __restrict__ wf_flat, bf16* __restrict__ wd_flat,
+                                                                 const int64_t* __restrict__ desc, int n_desc) {
+    __shared__ bf16 tile[32][33];
+    const int64_t t = blockIdx.x;
+    int lo = 0, hi = n_desc - 1;
+    while (lo < hi) {                                   // last descriptor whose first tile is <= t
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(desc + 5 * mid + 4) <= t) lo = mid; else hi = mid - 1;
+    }
+    const int64_t* d = desc + 5 * lo;
+    const int64_t off = __ldg(d);
+    const int Cout = (int)__ldg(d + 1), Cin = (int)__ldg(d + 2), taps = (int)__ldg(d + 3);
+    const int tco = (Cout + 31) >> 5, tci = (Cin + 31) >> 5;
+    int r = (int)(t - __ldg(d + 4));
+    const int tap = r / (tco * tci);
+    r -= tap * tco * tci;
+    const int co0 = (r % tco) * 32, ci0 = (r / tco) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const bf16* src = wf_flat + off + (int64_t)tap * Cout * Cin;
+    bf16* dst = wd_flat + off + (int64_t)(taps - 1 - tap) * Cin * Cout;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int co = co0 + ty + i, ci = ci0 + tx;
+        if (co < Cout && ci < Cin) tile[ty + i][tx] = src[(int64_t)co * Cin + ci];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int ci = ci0 + ty + i, co = co0 + tx;
+        if (co < Cout && ci < Cin) dst[(int64_t)ci * Cout + co] = tile[tx][ty + i];
+    }
+}
+
+DMVAE_API int dmvae_pack_dgrad_batched(const void* w_fwd_flat, void* w_dgrad_flat, const int64_t* desc, int n_desc, int64_t total_tiles,
+                                       void* stream) {
+    DMVAE_CHECK_ARG(n_desc >= 0 && total_tiles >= 0 && total_tiles < (int64_t)1 << 31, "pack_dgrad_batched: bad size");
+    if (n_desc == 0 || total_tiles == 0) return DMVAE_OK;
+    DMVAE_CHECK_ARG(w_fwd_flat && w_dgrad_flat && desc, "pack_dgrad_batched: null pointer");
+    pack_dgrad_batched_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>((const bf16*)w_fwd_flat, (bf16*)w_dgrad_flat, desc, n_desc);
+    DMVAE_CHECK_LAUNCH("pack_dgrad_batched_kernel");
+    return DMVAE_OK;
+}
+
 // tap-major wgrad scratch [tap][Cout][Cin] -> state_dict layout dw[co][ci][tap] (accumulate=1: +=).
 // One CTA per (co, 256-wide ci chunk): taps coalesced row reads, shared-memory interleave, one contiguous write.
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restrict__ dwp, float* __restrict__ dw,

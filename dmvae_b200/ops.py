@@ -28,6 +28,54 @@ import os as _os
 FUSE_GN_STATS_MIN_CPG = int(_os.environ.get("DMVAE_FUSE_GN_STATS_MIN_CPG", "4"))
 
 
+class ZeroPool:
+    """Bump allocator over a buffer its owner zero-fills once per training step, for the many small accumulators a step needs
+    (GroupNorm statistics, the group sums of its backward, affine / bias gradients: ~150 tensors of a few KB) -- instead of one
+    ``torch.zeros`` fill kernel each.  GradArena owns one: the pool is the tail of the gradient buffer's allocation, so the
+    arena's per-step ``zero()`` clears it in the same memset.  Allocations come from the pool only inside ``with pool:`` (a
+    trainer's forward + backward); tensors handed out are valid until the owner's next ``zero()`` -- every user consumes them
+    within the step (statistics saved for backward included).  A full pool falls back to ``torch.zeros``."""
+    current: Optional["ZeroPool"] = None
+    enabled = bool(int(_os.environ.get("DMVAE_ZERO_POOL", "1")))
+
+    def __init__(self, buf: torch.Tensor):
+        self.buf = buf.view(torch.uint8)
+        self.off = 0
+        self.high_water = 0
+        self._prev: Optional["ZeroPool"] = None
+
+    def reset(self) -> None:
+        """The owner has just zero-filled the buffer."""
+        self.off = 0
+
+    def __enter__(self):
+        self._prev, ZeroPool.current = ZeroPool.current, (self if ZeroPool.enabled else None)
+        return self
+
+    def __exit__(self, *exc):
+        ZeroPool.current = self._prev
+        return False
+
+
+def small_zeros(shape, dtype, device) -> torch.Tensor:
+    """Zero-filled tensor for a per-step accumulator: carved out of the active ZeroPool when there is one."""
+    pool = ZeroPool.current
+    if pool is not None and pool.buf.device == device:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = (n * dtype.itemsize + 31) // 32 * 32
+        if pool.off + nbytes <= pool.buf.numel():
+            # a fresh tensor over the pool's storage, NOT a view of it: views share one autograd version counter, and any
+            # in-place write to the arena (its memset, AccumulateGrad's +=) would invalidate every pool tensor saved for backward
+            t = torch.empty((0,), dtype=dtype, device=device).set_(
+                pool.buf.untyped_storage(), (pool.buf.storage_offset() + pool.off) // dtype.itemsize, tuple(int(d) for d in shape))
+            pool.off += nbytes
+            pool.high_water = max(pool.high_water, pool.off)
+            return t
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
 def _chk_nhwc(x: torch.Tensor, name: str) -> torch.Tensor:
     if x.dtype != torch.bfloat16 or x.ndim != 4:
         raise _lib.DmvaeError(f"{name}: expected a (B,H,W,C) bfloat16 tensor, got {tuple(x.shape)} {x.dtype}")
@@ -56,8 +104,10 @@ class WeightPack:
                 # the optimizer kernel keeps a bf16 copy of this (tap-major) parameter: that IS w_fwd; only the transposed
                 # data-gradient operand is derived here, bf16 -> bf16 (optim.FlatAdamWEMA, csrc/optim.cu)
                 taps, cout, cin = w16.shape
-                wd = torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=w16.device)
-                call("dmvae_pack_dgrad_bf16", ptr(w16), ptr(wd), cout, cin, taps)
+                wd = getattr(weight, "_dmvae_wd16", None)          # ... or not even that: the optimizer's batched transpose
+                if wd is None:
+                    wd = torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=w16.device)
+                    call("dmvae_pack_dgrad_bf16", ptr(w16), ptr(wd), cout, cin, taps)
                 self.w_fwd, self.w_dgrad, self.version, self.data_ptr = w16, wd, v, weight.data_ptr()
                 return self.w_fwd, self.w_dgrad
             w = weight.detach()
@@ -97,7 +147,7 @@ def conv_forward_raw(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[tor
         stats = None
         if want_gn_stats and cout % 32 == 0 and cout // 32 >= FUSE_GN_STATS_MIN_CPG and \
                 (cout // 32 in (1, 2, 4, 8, 16) or (cout // 32) % 32 == 0):
-            stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
+            stats = small_zeros((B, 32, 2), torch.float64, x.device)
         call("dmvae_conv_tc_fwd", ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(y), ptr(stats), B, H, W, cin, cout, kh, kw, flags)
         if stats is not None:
             y._dmvae_gnstats = (stats, y.data_ptr(), tuple(y.shape), _ver(y))       # consumed by the next GroupNorm
@@ -231,7 +281,7 @@ def bias_grad_raw(dy: torch.Tensor, out: Optional[torch.Tensor] = None) -> Optio
     if out is not None:
         call("dmvae_bias_grad", ptr(dy), ptr(out), dy.numel() // c, c)
         return None
-    db = torch.zeros((c,), dtype=torch.float32, device=dy.device)
+    db = small_zeros((c,), torch.float32, dy.device)
     call("dmvae_bias_grad", ptr(dy), ptr(db), dy.numel() // c, c)
     return db
 
@@ -245,7 +295,7 @@ def _tagged_gn_stats(x: torch.Tensor) -> Optional[torch.Tensor]:
 
 def gn_stats_raw(x: torch.Tensor) -> torch.Tensor:
     B, H, W, c = x.shape
-    stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
+    stats = small_zeros((B, 32, 2), torch.float64, x.device)
     call("dmvae_gn_stats", ptr(x), ptr(stats), B, H * W, c)
     return stats
 
@@ -262,10 +312,10 @@ def gn_bwd_raw(da, x, stats, gamma, beta, silu: bool, dres=None, eps: float = GN
     """Returns (dx, dgamma, dbeta); with ``out_dgamma`` / ``out_dbeta`` (fp32 [C]) the affine gradients are accumulated into them
     (the kernel adds atomically) and None is returned in their place."""
     B, H, W, c = x.shape
-    gsum = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
+    gsum = small_zeros((B, 32, 2), torch.float64, x.device)
     # one zero-filled fp32 buffer for dgamma | dbeta | column sums
     direct = out_dgamma is not None and out_dbeta is not None
-    small = torch.zeros((1 if direct else 3, c), dtype=torch.float32, device=x.device)
+    small = small_zeros((1 if direct else 3, c), torch.float32, x.device)
     dgamma, dbeta, colsum = (out_dgamma, out_dbeta, small[0]) if direct else (small[0], small[1], small[2])
     dx = torch.empty_like(x)
     call("dmvae_gn_bwd", ptr(da), ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(gsum), ptr(dgamma), ptr(dbeta), ptr(dres),
@@ -591,7 +641,7 @@ class UpsampleConvFn(torch.autograd.Function):
         y = torch.empty((B, 2 * H, 2 * W, cout), dtype=torch.bfloat16, device=x.device)
         stats = None
         if want_gn_stats and cout // 32 in (4, 8, 16) and cout % 32 == 0 and cout // 32 >= FUSE_GN_STATS_MIN_CPG:
-            stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x.device)
+            stats = small_zeros((B, 32, 2), torch.float64, x.device)
         b = None if bias is None else bias.detach()
         if b is not None and b.dtype != torch.float32:
             b = b.float()

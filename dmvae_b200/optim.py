@@ -13,6 +13,7 @@ the EMA views with the module's frozen parameters and buffers into a dict that `
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterable, List, Optional
 
 import torch
@@ -44,11 +45,25 @@ class FlatAdamWEMA:
         # bf16 copy of the parameters, rewritten by the optimizer kernel: for conv weights (tap-major, or 1x1) the view
         # [taps][Cout][Cin] of it IS the conv tiles' packed forward operand (ops.WeightPack picks it up through p._dmvae_w16)
         self.w16 = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        # ... and its per-tap transpose [taps-1-tap][Cin][Cout], the data-gradient operand, at the same offsets of a second
+        # arena: rebuilt for ALL conv weights by one batched launch after the update (DMVAE_BATCHED_DGRAD_PACK=0: ops.WeightPack
+        # derives it per layer, one small launch each, the first time a step uses the weight)
+        batched = bool(int(os.environ.get("DMVAE_BATCHED_DGRAD_PACK", "1")))
+        self.wd16 = torch.zeros(n if batched else 0, dtype=torch.bfloat16, device=dev)
+        desc, tiles = [], 0
         for p, off in zip(self.params, self.arena.offsets):
             if p.ndim == 4 and (p.shape[2] * p.shape[3] == 1 or (p.shape[2] == 3 and p.shape[3] == 3)):
                 co, ci, kh, kw = p.shape
                 p._dmvae_w16 = self.w16[off:off + p.numel()].view(kh * kw, co, ci)
                 p._dmvae_w16_version = -1
+                if batched:
+                    p._dmvae_wd16 = self.wd16[off:off + p.numel()].view(kh * kw, ci, co)
+                    desc.append((off, co, ci, kh * kw, tiles))
+                    tiles += kh * kw * ((co + 31) // 32) * ((ci + 31) // 32)
+                elif hasattr(p, "_dmvae_wd16"):
+                    del p._dmvae_wd16
+        self._pack_desc = torch.tensor(desc, dtype=torch.int64, device=dev).reshape(-1, 5) if desc else None
+        self._pack_tiles = tiles
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.ema_decay = 0.0 if ema_decay is None else ema_decay
         self.t = 0
@@ -62,9 +77,15 @@ class FlatAdamWEMA:
         ``load_state_dict``, before a CUDA-graph capture).  Until this or the next ``step()`` runs, ops.WeightPack sees a stale
         version stamp and packs from the fp32 parameter itself."""
         call("dmvae_cast_bf16", ptr(self.flat_p), ptr(self.w16), self.flat_p.numel())
+        self._pack_dgrad()
         for p in self.params:
             if hasattr(p, "_dmvae_w16"):
                 p._dmvae_w16_version = p._version
+
+    def _pack_dgrad(self) -> None:
+        if self._pack_desc is not None:
+            call("dmvae_pack_dgrad_batched", ptr(self.w16), ptr(self.wd16), ptr(self._pack_desc), self._pack_desc.shape[0],
+                 self._pack_tiles)
 
     def sync_ema(self) -> None:
         """EMA := current weights.  The reference deep-copies the model into ``vae_ema`` after the weights are in place
@@ -86,6 +107,7 @@ class FlatAdamWEMA:
         call("dmvae_adamw_ema_step", ptr(self.flat_p), ptr(self.arena.flat), ptr(self.m), ptr(self.v), ptr(self.ema), ptr(self.w16),
              ptr(self._sumsq), ptr(self._norm), n, float(self.lr if lr is None else lr), float(self.betas[0]),
              float(self.betas[1]), float(self.eps), float(self.wd), int(self.t), float(self.max_norm), float(self.ema_decay))
+        self._pack_dgrad()
         torch.autograd.graph.increment_version(self.params)      # the kernel wrote through raw pointers
         for p in self.params:
             if hasattr(p, "_dmvae_w16"):

@@ -358,11 +358,12 @@ class TokenizerTrainer:
 
     def _decode_backward(self, images: torch.Tensor, tokens: torch.Tensor) -> Dict[str, torch.Tensor]:
         self.arena.zero()
-        with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
-            recon = self.vae.decoder(self.vae.bottle_neck(tokens)).float()      # models/vae.py:94-97
-            loss, log = self.loss_fn.forward_generator(images, recon, step=self.global_step)
-        with self.arena.direct():
-            loss.backward()
+        with self.arena.scratch():                  # small per-step accumulators come out of the arena's zero pool
+            with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
+                recon = self.vae.decoder(self.vae.bottle_neck(tokens)).float()      # models/vae.py:94-97
+                loss, log = self.loss_fn.forward_generator(images, recon, step=self.global_step)
+            with self.arena.direct():
+                loss.backward()
         log["loss"] = loss.detach()
         return log
 
@@ -376,11 +377,12 @@ class TokenizerTrainer:
 
     def _forward_backward(self, images: torch.Tensor, exchange: bool = True) -> Dict[str, torch.Tensor]:
         self.arena.zero()
-        with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
-            recon = self.vae(images, freeze_encoder=True)
-            loss, log = self.loss_fn.forward_generator(images, recon, step=self.global_step)
-        with self.arena.direct():                   # conv / GroupNorm gradients accumulate straight into the arena
-            loss.backward()
+        with self.arena.scratch():                  # small per-step accumulators come out of the arena's zero pool
+            with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
+                recon = self.vae(images, freeze_encoder=True)
+                loss, log = self.loss_fn.forward_generator(images, recon, step=self.global_step)
+            with self.arena.direct():               # conv / GroupNorm gradients accumulate straight into the arena
+                loss.backward()
         if exchange:
             self.arena.allreduce()                  # chunks not yet launched from the hooks, wait, (average inside NCCL)
         log["loss"] = loss.detach()
@@ -546,14 +548,15 @@ class DmdTrainer:
         for p in self.sit.parameters():
             p.requires_grad = False
         self.arena_vae.zero()
-        with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
-            recon, z = self.vae(images, return_latent=True)
-            latents = self._latents(z)
-            if t_dmd is None:
-                t_dmd = self._draw_t(latents)
-            loss, log = self.loss_fn.forward_generator(images, recon, latents, labels, compute_dmd=self.cfg.dmd_weight > 0, t=t_dmd)
-        with self.arena_vae.direct():
-            loss.backward()
+        with self.arena_vae.scratch():
+            with torch.autocast(device_type=images.device.type, dtype=torch.bfloat16):
+                recon, z = self.vae(images, return_latent=True)
+                latents = self._latents(z)
+                if t_dmd is None:
+                    t_dmd = self._draw_t(latents)
+                loss, log = self.loss_fn.forward_generator(images, recon, latents, labels, compute_dmd=self.cfg.dmd_weight > 0, t=t_dmd)
+            with self.arena_vae.direct():
+                loss.backward()
         if exchange:
             self.arena_vae.allreduce()
         log["loss"] = loss.detach()

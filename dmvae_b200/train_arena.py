@@ -44,6 +44,8 @@ class GradArena:
     replayed CUDA graph only re-runs the captured ``flat.zero_()`` kernel) still exchanges every chunk on every step.
     On NCCL the average is taken inside the collective (ReduceOp.AVG): no separate division pass."""
 
+    SCRATCH_BYTES = 4 << 20     # zero pool behind the gradients (ops.ZeroPool): cleared by the same memset as the arena
+
     def __init__(self, params: Iterable[nn.Parameter], chunks: int = 4, overlap: bool = True):
         self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
         self.offsets: List[int] = []
@@ -52,7 +54,11 @@ class GradArena:
             self.offsets.append(n)
             n += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)      # padding elements stay zero (and inert in the optimizer)
+        tail = self.SCRATCH_BYTES // 4 if dev.type == "cuda" else 0
+        self._storage = torch.zeros(n + tail, dtype=torch.float32, device=dev)
+        self.flat = self._storage[:n]                                    # padding elements stay zero (and inert in the optimizer)
+        from .ops import ZeroPool
+        self.pool = ZeroPool(self._storage[n:])
         self.chunks = max(1, min(chunks, len(self.params) or 1))
         # chunk boundaries on parameter boundaries, roughly equal in bytes
         target = (n + self.chunks - 1) // self.chunks
@@ -118,9 +124,15 @@ class GradArena:
         self._ready = set()
 
     def zero(self):
-        self.flat.zero_()
+        self._storage.zero_()               # gradients + the zero pool behind them
+        self.pool.reset()
         self._attach()
         self.begin_step()
+
+    def scratch(self):
+        """Context manager for one forward + backward that started with ``zero()``: the pass's small zero-initialised
+        accumulators (GroupNorm statistics, ...) are carved out of the pool this arena clears, not filled one by one."""
+        return self.pool
 
     def _launch(self, c: int):
         s, e = self.bounds[c]

@@ -34,7 +34,7 @@ extern "C" {
 
 /* Bumped whenever a prototype below changes; the ctypes binding (dmvae_b200/_lib.py) refuses a library whose
  * dmvae_abi_version() differs from the table it was written against. */
-#define DMVAE_ABI_VERSION 7
+#define DMVAE_ABI_VERSION 8
 
 const char* dmvae_last_error(void);
 int dmvae_abi_version(void);
@@ -115,6 +115,11 @@ int dmvae_pack_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int
                        void* stream);
 /* w_dgrad from an existing bf16 w_fwd (the optimizer kernel maintains w_fwd for tap-major parameter arenas, see N2). */
 int dmvae_pack_dgrad_bf16(const void* w_fwd, void* w_dgrad, int Cout, int Cin, int taps, void* stream);
+/* The same for every conv weight of a flat bf16 parameter arena in ONE launch (issued by the optimizer after its update kernel).
+ * desc: device int64 [n_desc][5] = {element offset of the parameter in both arenas, Cout, Cin, taps, index of its first 32x32
+ * tile}, first-tile indices ascending from 0; total_tiles = sum over parameters of taps * ceil(Cout/32) * ceil(Cin/32). */
+int dmvae_pack_dgrad_batched(const void* w_fwd_flat, void* w_dgrad_flat, const int64_t* desc, int n_desc, int64_t total_tiles,
+                             void* stream);
 
 /* 1 if the shape runs on the tcgen05 tile (stride 1, 3x3 pad 1 or 1x1, C%8==0, pixel tile divides H,W). */
 int dmvae_conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW);

@@ -291,6 +291,49 @@ def test_grad_arena_layout_tap_major_views_and_padding():
     assert torch.allclose(w3.grad, ref) and w3.grad.data_ptr() == arena.flat.data_ptr() + 4 * arena.offsets[0]
 
 
+def test_zero_pool_tensors_have_their_own_version_counters():
+    """ops.ZeroPool hands out accumulators that alias the tail of the gradient arena's allocation.  They must NOT be views of it:
+    views share one autograd version counter, so the arena's memset or an AccumulateGrad ``+=`` into any gradient slot would
+    invalidate every pool tensor saved for backward (host logic only, exercised on a CPU buffer)."""
+    from dmvae_b200 import ops
+    storage = torch.zeros(1000 + 256, dtype=torch.float32)
+    flat, pool = storage[:1000], ops.ZeroPool(storage[1000:])
+
+    class Scale(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            acc = ops.small_zeros((3, 2), torch.float64, x.device)
+            acc += x.sum().double()
+            ctx.save_for_backward(acc)
+            return x * 2
+
+        @staticmethod
+        def backward(ctx, g):
+            (acc,) = ctx.saved_tensors
+            return g * 2 + acc[0, 0].float()
+
+    x = torch.ones(4, requires_grad=True)
+    outside = ops.small_zeros((5,), torch.float32, x.device)
+    with pool:
+        y = Scale.apply(x)
+        b = ops.small_zeros((5,), torch.float32, x.device)
+        assert b.data_ptr() == storage.data_ptr() + 4000 + 64 and pool.off == 96          # 32-byte granules
+        b.fill_(3.0)
+        flat.add_(1.0)                     # what AccumulateGrad / the memset do to the shared allocation
+        storage[1000:].add_(0.0)
+        y.sum().backward()                 # would raise "modified by an inplace operation" for a view
+        too_big = ops.small_zeros((4096,), torch.float32, x.device)
+    assert torch.equal(x.grad, torch.full((4,), 6.0))
+    assert not storage.data_ptr() <= outside.data_ptr() < storage.data_ptr() + 4 * storage.numel()
+    assert not storage.data_ptr() <= too_big.data_ptr() < storage.data_ptr() + 4 * storage.numel()
+    assert ops.ZeroPool.current is None
+    assert torch.equal(storage[1016:1021], torch.full((5,), 3.0))
+    storage.zero_(); pool.reset()
+    with pool:
+        again = ops.small_zeros((3, 2), torch.float64, x.device)
+    assert again.data_ptr() == storage.data_ptr() + 4000 and float(again.abs().sum()) == 0.0
+
+
 def test_shutdown_distributed_without_process_group_is_a_noop():
     from dmvae_b200.train import shutdown_distributed
 

@@ -3,6 +3,7 @@ CPU oracle run in its autocast-emulating mode (bf16=True) on identical weights a
 
 Tolerance: activations are bf16 (ulp 2^-8 = 3.9e-3); through a stack of L conv+GN layers independent roundings add
 in quadrature, so norm-wise relative error is bounded by ~2^-8*sqrt(L): 2e-2 for the decoders here."""
+import contextlib
 import copy
 import os
 
@@ -472,6 +473,20 @@ def test_optimizer_maintained_weight_packs_and_tap_major_arena():
     opt.sync_w16()                                                        # the copy is current again: a pack built now picks it up
     wf, _ = ops.WeightPack().get(w3)
     assert wf.data_ptr() == w3._dmvae_w16.data_ptr() and torch.equal(wf, rf)
+    wf, wd = ops.WeightPack().get(w3)
+    assert wd.data_ptr() == w3._dmvae_wd16.data_ptr() and torch.equal(wd, rd)      # the batched transpose, not a per-layer pack
+    # the batched transpose over ragged shapes (tiles that overhang Cout / Cin, several parameters per launch)
+    odd = torch.nn.Sequential(torch.nn.Conv2d(40, 3, 3), torch.nn.Conv2d(72, 40, 1), torch.nn.Conv2d(8, 200, 3), torch.nn.Linear(5, 7)).to(DEV)
+    opt_odd = FlatAdamWEMA(odd.parameters(), lr=1e-2)
+    for it in range(2):
+        for m in list(odd)[:3]:
+            wf, wd = ops.WeightPack().get(m.weight)
+            rf, rd = plain(m.weight)
+            assert wd.data_ptr() == m.weight._dmvae_wd16.data_ptr() and torch.equal(wf, rf) and torch.equal(wd, rd), (it, m)
+        opt_odd.arena.zero()
+        for p in opt_odd.params:
+            p.grad.copy_(torch.randn(p.shape, device=DEV))
+        opt_odd.step()
     # checkpoint surface
     sd = net.state_dict()
     assert sd["0.weight"].shape == (128, 64, 3, 3)
@@ -614,6 +629,53 @@ def test_direct_param_grads_match_autograd_accumulation():
     assert w.grad.stride() != w.grad.contiguous().stride()
     flat_slot = arena.flat[arena.offsets[[id(q) for q in arena.params].index(id(w))]:][:w.numel()].view(9, w.shape[0], w.shape[1])
     assert torch.equal(flat_slot.permute(1, 2, 0).reshape(w.shape), w.grad.contiguous())
+
+
+def test_zero_pool_accumulators_are_zero_aligned_and_the_same_training():
+    """GradArena.scratch(): the per-step accumulators carved out of the arena's zero pool must be zero-filled after zero(),
+    32-byte aligned, disjoint, fall back to torch.zeros when the pool is full or not active, and give the same gradients as
+    individually filled tensors."""
+    from dmvae_b200 import ops
+    from dmvae_b200.autoencoder import Decoder
+    from dmvae_b200.train_arena import GradArena
+    torch.manual_seed(5)
+    dec = Decoder(ch=32, out_ch=3, ch_mult=(1, 2), num_res_blocks=1, in_channels=3, resolution=32, z_channels=4).to(DEV)
+    arena = GradArena(dec.parameters())
+    z = torch.randn(2, 4, 16, 16, device=DEV)
+    lo, hi = arena.pool.buf.data_ptr(), arena.pool.buf.data_ptr() + arena.pool.buf.numel()
+    assert lo == arena.flat.data_ptr() + 4 * arena.flat.numel() and lo % 32 == 0
+
+    dev = z.device                                                 # call sites pass a tensor's device
+    outside = ops.small_zeros((3, 5), torch.float32, dev)
+    assert not lo <= outside.data_ptr() < hi                       # no active pool: an ordinary tensor
+    arena.zero()
+    with arena.scratch():
+        a = ops.small_zeros((2, 32, 2), torch.float64, dev)
+        b = ops.small_zeros((3, 7), torch.float32, dev)
+        big = ops.small_zeros((arena.pool.buf.numel(),), torch.uint8, dev)      # does not fit any more
+        a.fill_(1.0); b.fill_(2.0)
+    assert a.data_ptr() == lo and b.data_ptr() == lo + 1024 and b.data_ptr() % 32 == 0
+    assert not lo <= big.data_ptr() < hi and int(big.sum()) == 0
+    arena.zero()
+    with arena.scratch():
+        a2 = ops.small_zeros((2, 32, 2), torch.float64, dev)
+    assert a2.data_ptr() == lo and float(a2.abs().sum()) == 0.0 and float(b.abs().sum()) == 0.0
+
+    def run(pooled):
+        arena.zero()
+        ctx = arena.scratch() if pooled else contextlib.nullcontext()
+        with ctx:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = dec(z).float().square().mean()
+            with arena.direct():
+                loss.backward()
+        torch.cuda.synchronize()
+        return arena.flat.clone(), arena.pool.off
+
+    (ref, used0), (got, used1) = run(False), run(True)
+    assert used0 == 0 and used1 > 0
+    noise = rel(run(False)[0], ref)
+    assert rel(got, ref) < max(5 * noise, 5e-3), (rel(got, ref), noise)
 
 
 def test_tokenizer_trainer_cuda_graph_matches_eager():
