@@ -334,6 +334,36 @@ def test_zero_pool_tensors_have_their_own_version_counters():
     assert again.data_ptr() == storage.data_ptr() + 4000 and float(again.abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("tag", ["w0.5_bcr4", "w0.1_l2_bcr0"])
+def test_discriminator_turn_against_reference_golden(tag):
+    """VAELossFunction.forward_discriminator is host-side composition of stock ops (no library kernel), so it is pinned here,
+    on the CPU, to the reference method's outputs (train_dmd.py:265-285, tests/golden/make_golden_gan.py); the generator turn,
+    whose L1 / L2 come from the fused kernel, is pinned by the GPU suite against the same fixture."""
+    import importlib.util
+    from dmvae_b200.train import LossConfig, VAELossFunction
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_gan", os.path.join(here, "golden", "make_golden_gan.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    fx = torch.load(os.path.join(here, "golden", "gan.pt"), weights_only=False)[tag]
+    last = torch.nn.Conv2d(6, 3, 3, padding=1)
+    last.load_state_dict(fx["last_sd"])
+    disc = G.TinyDisc()
+    disc.load_state_dict(fx["disc_sd"])
+    lf = VAELossFunction(LossConfig(disc_weight=fx["disc_weight"], bcr=fx["bcr"]), disc=disc, last_layer=last.weight,
+                         aug=lambda x, fade=0.0: x, bcr_aug=lambda x, fade=0.0: x.flip(-1))
+    with torch.no_grad():
+        recon = last(fx["h"])
+    d_loss, d_log = lf.forward_discriminator(fx["images"], recon)
+    grads = torch.autograd.grad(d_loss, list(disc.parameters()))
+    assert disc.training and all(p.requires_grad for p in disc.parameters())
+    assert abs(d_loss.item() - fx["d_loss"].item()) < 1e-6
+    for k in ("d_loss", "acc_real", "acc_fake") + (("bcr_loss",) if fx["bcr"] > 0 else ()):
+        assert abs(float(d_log[k]) - fx["d_log"][k]) < 1e-5 * max(abs(fx["d_log"][k]), 1.0), k
+    for (n, _), g in zip(disc.named_parameters(), grads):
+        assert torch.allclose(g, fx["d_params"][n], rtol=1e-5, atol=1e-7), n
+
+
 def test_shutdown_distributed_without_process_group_is_a_noop():
     from dmvae_b200.train import shutdown_distributed
 

@@ -261,6 +261,55 @@ def test_gan_iteration_adaptive_weight_eager_and_graph():
         assert abs(le["d_loss"].item() - lg["d_loss"].item()) <= 2e-2 * abs(le["d_loss"].item()) + 1e-3
 
 
+def _gan_standins():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_gan", os.path.join(os.path.dirname(__file__), "golden", "make_golden_gan.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)            # only its main() reads the reference tree
+    return m
+
+
+@pytest.mark.parametrize("tag", ["w0.5_bcr4", "w0.1_l2_bcr0", "not_started"])
+def test_gan_branch_against_reference_golden(tag):
+    """BASELINE configs[3]: VAELossFunction.forward_generator / forward_discriminator against the outputs of the reference's own
+    methods (train_dmd.py:232-285, cut from the source and executed by tests/golden/make_golden_gan.py): L1 / L2 from the fused
+    kernel, the adaptive GAN weight from the two retain_graph autograd.grad calls, the total loss and its gradients at the last
+    layer and at the decoder features; hinge loss, accuracies and BCR of the discriminator turn.  fp32 on both sides (TF32 off):
+    1e-4 on scalars and norm-wise on gradients (the d_weight ratio amplifies summation-order noise of two gradient norms)."""
+    from dmvae_b200.train import LossConfig, VAELossFunction
+    G = _gan_standins()
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "gan.pt"), map_location=DEV, weights_only=False)[tag]
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        last = torch.nn.Conv2d(6, 3, 3, padding=1).to(DEV)
+        last.load_state_dict(fx["last_sd"])
+        disc = G.TinyDisc().to(DEV)
+        disc.load_state_dict(fx["disc_sd"])
+        cfg = LossConfig(l1=1.0, l2=fx["l2"], lpips=1.0, disc_weight=fx["disc_weight"], disc_start_step=fx["disc_start_step"], bcr=fx["bcr"])
+        lf = VAELossFunction(cfg, lpips_loss=G.lpips_standin, disc=disc, last_layer=last.weight,
+                             aug=lambda x, fade=0.0: x, bcr_aug=lambda x, fade=0.0: x.flip(-1))
+        h = fx["h"].clone().requires_grad_(True)
+        recon = last(h)
+        loss, log = lf.forward_generator(fx["images"], recon, step=fx["step"])
+        d_last, d_h = torch.autograd.grad(loss, [last.weight, h])
+        assert abs(loss.item() - fx["loss"].item()) < 1e-4 * abs(fx["loss"].item())
+        assert set(log) == set(fx["log"])                              # d_weight only once the discriminator has started
+        for k, v in fx["log"].items():
+            assert abs(float(log[k]) - v) < 1e-4 * max(abs(v), 1e-3), (k, float(log[k]), v)
+        assert rel(d_last, fx["d_last"]) < 1e-4 and rel(d_h, fx["d_h"]) < 1e-4
+        assert all(not p.requires_grad for p in disc.parameters()) == (fx["step"] >= fx["disc_start_step"])
+        d_loss, d_log = lf.forward_discriminator(fx["images"], recon.detach())
+        grads = torch.autograd.grad(d_loss, list(disc.parameters()))
+        assert abs(d_loss.item() - fx["d_loss"].item()) < 1e-4 * abs(fx["d_loss"].item())
+        for k in ("d_loss", "acc_real", "acc_fake") + (("bcr_loss",) if fx["bcr"] > 0 else ()):
+            assert abs(float(d_log[k]) - fx["d_log"][k]) < 1e-4 * max(abs(fx["d_log"][k]), 1e-3), k
+        for (n, _), g in zip(disc.named_parameters(), grads):
+            assert rel(g, fx["d_params"][n]) < 1e-4, n
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+
+
 def test_loss_curve_parity_real_trainer_vs_stock_arms():
     """12 steps of the REAL TokenizerTrainer (CUDA-graph replay, arena, fused clip + AdamW + EMA; ViT-B encoder, production decoder)
     against the strict-fp32 stock-PyTorch anchor and the cuDNN-autocast control arm (scripts/loss_parity.py, scripts/stock_arms.py).
