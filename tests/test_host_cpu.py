@@ -161,6 +161,39 @@ for it in range(3):
     arena.allreduce()
     assert arena.exchanges - n0 == len(arena.bounds), (it, arena.exchanges - n0)
     assert torch.allclose(arena.flat, ref, rtol=1e-5, atol=1e-7), it
+# pipelined exchange (TokenizerTrainer with several ranks): step k's local gradients stay in the arena; step k+1 begins with
+# launch_all(), does other work (the frozen-encoder forward) while the all-reduces run, then finish() + the weight update, and only
+# then zero()s the arena for its own backward.  Two ranks on half batches must train exactly like one process on the full batch.
+import copy
+solo = copy.deepcopy(net)
+lr = 0.1
+pending = False
+for it in range(3):
+    xs = torch.randn(8, 8, generator=g)
+    if pending:                                   # ---- start of step `it`: finish step it-1
+        n0 = arena.exchanges
+        arena.launch_all()
+        assert arena.exchanges - n0 == len(arena.bounds)
+        busy = torch.tanh(xs).sum()               # stands for the encoder forward that overlaps the exchange
+        arena.finish()
+        assert not any(arena._launched) and arena._handles == [], "finish() must leave the bookkeeping reset"
+        with torch.no_grad():
+            for p_ in net.parameters():
+                p_.sub_(lr * p_.grad)
+    arena.zero()
+    net(xs[rank * 4:(rank + 1) * 4]).square().mean().backward()
+    assert not any(arena._launched), "pipelined mode: nothing is exchanged from backward"
+    pending = True
+    gs = torch.autograd.grad(solo(xs).square().mean(), list(solo.parameters()))       # the sequential single-process run
+    with torch.no_grad():
+        for p_, g_ in zip(solo.parameters(), gs):
+            p_.sub_(lr * g_)
+arena.allreduce()                                 # flush(): the last step's update
+with torch.no_grad():
+    for p_ in net.parameters():
+        p_.sub_(lr * p_.grad)
+for p_, q_ in zip(net.parameters(), solo.parameters()):
+    assert torch.allclose(p_, q_, rtol=1e-5, atol=1e-7), (p_ - q_).abs().max()
 dist.destroy_process_group()
 print("OK", rank)
 '''
